@@ -1,0 +1,165 @@
+/*
+ * specdec_b200.h -- C ABI of libspecdec_b200.so (sm_100a), the drop-in boundary for the
+ * speculative-sampling verify hot path of dadiaokua/speculative-decoding.
+ *
+ * The reference has no FFI (it is pure Python over torch); each entry point
+ * below names the reference Python interface it replaces (paths relative to the reference
+ * tree).  INTEGRATION.md shows the ctypes / torch.library binding a maintainer adds.
+ *
+ * Conventions: every function returns 0 on success, <0 for an invalid argument
+ * (SPECDEC_ERR_*), >0 for a cudaError_t.  Nothing throws, nothing allocates (the caller
+ * passes workspace), nothing synchronises: all work is enqueued on `stream`.  All pointers
+ * are DEVICE pointers unless named host_*.  Strides are in ELEMENTS.  Logits are read-only
+ * (unlike TopKProcessor._process, utils/logits_processor.py:62, which mutates its input).
+ */
+#ifndef SPECDEC_B200_H
+#define SPECDEC_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct CUstream_st* specdec_stream_t; /* == cudaStream_t */
+
+#if defined(__GNUC__)
+#define SPECDEC_API __attribute__((visibility("default")))
+#else
+#define SPECDEC_API
+#endif
+
+/* logits dtypes */
+#define SPECDEC_F32 0
+#define SPECDEC_BF16 1
+#define SPECDEC_F16 2
+
+/* sample_mode: LogitsProcessor.sample() semantics */
+#define SPECDEC_SAMPLE_GREEDY 0 /* GreedyProcessor.sample: argmax, first index (utils/logits_processor.py:35-36) */
+#define SPECDEC_SAMPLE_INVCDF 1 /* Multinomial/TopK/Nucleus sample() restated as inverse CDF on an injected uniform */
+
+/* flags */
+#define SPECDEC_ACCEPT_BATCHED 1  /* accept iff u < (q<=0 ? 1 : min(1,p/q))  engine/infer_engine.py:303-305;
+                                     default: reject iff u > p/q             sampling/speculative_decoding.py:139-145 */
+#define SPECDEC_NO_BONUS 2        /* no bonus row; next_token=-1 when all accepted (engine/infer_engine.py:276) */
+#define SPECDEC_SKIP_ADJUST 4     /* skip_sample_adjustment (sampling/speculative_decoding.py:167-170) */
+#define SPECDEC_NGRAM 8           /* accept iff draft==sample(p_i); no drafter logits (ngram_assisted/ngram_assisted.py:114-141) */
+#define SPECDEC_RESID_FALLBACK 16 /* residual mass <= 1e-12 -> sample from p (engine/infer_engine.py:319-321) */
+
+#define SPECDEC_ERR_ARG (-1)
+#define SPECDEC_ERR_WORKSPACE (-2)
+#define SPECDEC_ERR_DTYPE (-3)
+#define SPECDEC_ERR_RANGE (-4)
+
+SPECDEC_API int specdec_version(void);
+SPECDEC_API const char* specdec_error_string(int code);
+
+/* Workspace needed by specdec_verify / specdec_process_probs / specdec_sample_rows for `rows`
+ * logit rows (verify: rows = B*(2*gamma+1)). */
+SPECDEC_API size_t specdec_workspace_bytes(int64_t rows);
+
+/*
+ * One speculative verify step for B sequences: replaces, per sequence,
+ *   p = logits_processor(target_logits[:, cp-1:cp+gamma-1])   sampling/speculative_decoding.py:135-136
+ *   q[0,k] = logits_processor(draft_logits_k)                  sampling/speculative_decoding.py:107,120-122
+ *   r = rand(gamma); fractions = p/q; first rejection n         :139-145
+ *   stop-token scan                                             :150-155
+ *   bonus (n==gamma) / max_fn(p[n]-q[n]) / skip adjustment; x = sample(p_p)   :158-171
+ * and, with SPECDEC_ACCEPT_BATCHED|SPECDEC_NO_BONUS|SPECDEC_RESID_FALLBACK, the batched
+ * loop body engine/infer_engine.py:276-336.  The processor is (temperature, top_k, top_p):
+ * top_k<=0 or >=V disables top-k, top_p<=0 or >=1 disables nucleus
+ * (utils/logits_processor.py:13-15,59-63,73-81,92-103).
+ *
+ * target_logits [B, gamma+1, V] (row gamma = bonus row; [B,gamma,V] suffices with NO_BONUS),
+ * draft_logits  [B, gamma, V]  (NULL with SPECDEC_NGRAM), draft_tokens [B,gamma] int64.
+ * u_accept [B,gamma], u_sample [B] in [0,1): if NULL they are Philox4x32-10 uniforms keyed
+ * by (philox_seed, philox_offset, seq_id0+b, position) -- independent of sharding.
+ * Outputs: n_accepted[B], next_token[B] (-1 if none), accept_mask[B,gamma] (per-position test,
+ * also past the first rejection), p_tok/q_tok[B,gamma] = P_i[tok_i], Q_i[tok_i],
+ * first_stop[B] = first accepted draft that is a stop token or -1,
+ * next_prob[B] (nullable) = probability of next_token under the distribution it was drawn from
+ * when that distribution is a processed target row, else 0,
+ * packed[B, gamma+2] int32 (nullable) = {n, tok_0..tok_{n-1}, next_token, -1...} for the
+ * multi-GPU all-gather.
+ */
+SPECDEC_API int specdec_verify(const void* target_logits, const void* draft_logits, int dtype,
+                   const int64_t* draft_tokens, const float* u_accept, const float* u_sample,
+                   uint64_t philox_seed, uint64_t philox_offset, int64_t seq_id0,
+                   int B, int gamma, int V,
+                   int64_t stride_tb, int64_t stride_tg, int64_t stride_db, int64_t stride_dg,
+                   float temperature, int top_k, float top_p, int sample_mode, int flags,
+                   const int64_t* stop_tokens, int n_stop,
+                   int32_t* n_accepted, int64_t* next_token, uint8_t* accept_mask,
+                   float* p_tok, float* q_tok, int32_t* first_stop, float* next_prob, int32_t* packed,
+                   void* workspace, size_t workspace_bytes, specdec_stream_t stream);
+
+/* Measurement hook (bench.py): when non-NULL, specdec_verify records these cudaEvent_t on its stream
+ * before the row-statistics kernel, between the two kernels and after the decide kernel. */
+SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end);
+
+/* LogitsProcessor.__call__ materialised: probs[rows,V] fp32 = softmax(_process(logits)/T)
+ * (utils/logits_processor.py:13-15).  row_stats (nullable) receives 8 floats per row:
+ * {max, S32, inv, cut, jcut, n/a, n/a, n/a}. */
+SPECDEC_API int specdec_process_probs(const void* logits, int dtype, int64_t rows, int V, int64_t stride,
+                          float temperature, int top_k, float top_p, float* probs, float* row_stats,
+                          void* workspace, size_t workspace_bytes, specdec_stream_t stream);
+
+/* processor + sample() fused for AR / drafter steps (sampling/base_decoding.py:51-57,
+ * sampling/speculative_decoding.py:120-124): tok[r] ~ processor(logits[r]); ptok[r] = its probability.
+ * u [rows] nullable (Philox keyed by seq_id0+r, lane 0x20000+lane_id). */
+SPECDEC_API int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int64_t stride,
+                        float temperature, int top_k, float top_p, int sample_mode, const float* u,
+                        uint64_t philox_seed, uint64_t philox_offset, int64_t seq_id0, int lane_id,
+                        int64_t* tok, float* ptok, void* workspace, size_t workspace_bytes,
+                        specdec_stream_t stream);
+
+/* LogitsProcessor.sample(probs) on materialised fp32 probabilities [rows,V]
+ * (utils/logits_processor.py:35-36 greedy, :48-49 restated as inverse CDF). */
+SPECDEC_API int specdec_sample_probs(const float* probs, int64_t rows, int V, int sample_mode, const float* u,
+                         int64_t* tok, specdec_stream_t stream);
+
+/* Dumps the exact uniforms specdec_verify would use (so tests can inject them into the oracle). */
+SPECDEC_API int specdec_philox_uniform(uint64_t seed, uint64_t offset, int64_t seq_id0, int B, int gamma,
+                           float* u_accept, float* u_sample, specdec_stream_t stream);
+
+/*
+ * Per-sequence KV rollback on a static cache: prune_cache / prune_tuple_cache
+ * (utils/caching.py:6-55; call sites sampling/speculative_decoding.py:163-165) generalised to a
+ * different discard count per sequence.  tensor_ptrs: DEVICE array of n_tensors device pointers,
+ * each a [B,H,S_max,D] tensor of elem_bytes-wide elements; seq_lens[B] in/out; the discarded
+ * positions are zero-filled when zero_fill!=0 (so the valid prefix equals the reference's view).
+ */
+SPECDEC_API int specdec_prune_kv(void* const* tensor_ptrs, int n_tensors, int B, int H, int64_t S_max, int64_t D,
+                     int elem_bytes, int32_t* seq_lens, const int32_t* discard, int zero_fill,
+                     specdec_stream_t stream);
+
+/*
+ * Device n-gram tables: NGramStorage / OneLevelNGramStorage (ngram_assisted/ngram_storage.py:73-249).
+ * One logical table per table id (sequence); capacity is per table.  `one_level`!=0 gives
+ * OneLevelNGramStorage semantics (single context length n-1).
+ * The handle is a host pointer; table memory is allocated once at create (cudaMalloc) -- the
+ * only allocation in the library, mirroring the reference's constructor.
+ */
+typedef struct specdec_ngram specdec_ngram_t;
+SPECDEC_API int specdec_ngram_create(specdec_ngram_t** out, int n, int vocab_size, int n_tables, int grams_per_table,
+                         int counts_per_table, int one_level);
+SPECDEC_API int specdec_ngram_destroy(specdec_ngram_t* t);
+SPECDEC_API int specdec_ngram_reset(specdec_ngram_t* t, specdec_stream_t stream);
+/* ids [B, max_len] int64 row-major with per-row valid length lens[B]; table_ids[B] (NULL = all table 0). */
+SPECDEC_API int specdec_ngram_initialize(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids,
+                             int B, int64_t max_len, specdec_stream_t stream);
+/* next_tokens [B, m] int64 */
+SPECDEC_API int specdec_ngram_update(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids,
+                         int B, int64_t max_len, const int64_t* next_tokens, int m, specdec_stream_t stream);
+/* gamma chained next_token() calls (ngram_assisted/ngram_assisted.py:95-99): drafts[B,gamma],
+ * known[B,gamma]; unknown positions take fallback[B,gamma] (the reference draws torch.randint). */
+SPECDEC_API int specdec_ngram_lookup_chain(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids,
+                               int B, int64_t max_len, int gamma, const int64_t* fallback, int64_t* drafts,
+                               uint8_t* known, specdec_stream_t stream);
+/* device int32[2]: {overflow flag, entries used (max over tables)} */
+SPECDEC_API int specdec_ngram_status(specdec_ngram_t* t, int32_t* host_out2);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

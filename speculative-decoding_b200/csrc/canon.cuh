@@ -1,0 +1,191 @@
+// canon.cuh -- canonical arithmetic + small device utilities shared by the sm_100a kernels.
+//
+// The verify path is specified in IEEE-754 fp32 (+,*,fma,/) and integer arithmetic only
+// (DESIGN.md section 3), so results are independent of launch geometry and reduction order and
+// are reproduced bit for bit by the CPU oracle.  Everything here uses explicit _rn
+// intrinsics (never contracted / reassociated by nvcc) and the library is built with
+// -fmad=false and without --use_fast_math.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace specdec {
+
+typedef unsigned long long u64;
+
+constexpr int DT_F32 = 0, DT_BF16 = 1, DT_F16 = 2;
+
+// 2^f on [-0.5,0.5], degree 5, p(0)=1; max rel. error 1.9e-7 in fp32 Horner/FMA evaluation.
+#define SPECDEC_C1 0x1.62e42ap-1f
+#define SPECDEC_C2 0x1.ebf9bcp-3f
+#define SPECDEC_C3 0x1.c6b752p-5f
+#define SPECDEC_C4 0x1.3cea88p-7f
+#define SPECDEC_C5 0x1.5bba14p-10f
+
+__device__ __forceinline__ float cexp2(float t) {
+  t = fmaxf(t, -125.0f);
+  t = fminf(t, 126.0f);
+  float r = __fadd_rn(t, 12582912.0f);
+  int i = __float_as_int(r) - 0x4B400000;
+  float fi = __fsub_rn(r, 12582912.0f);
+  float f = __fsub_rn(t, fi);
+  float p = SPECDEC_C5;
+  p = __fmaf_rn(p, f, SPECDEC_C4);
+  p = __fmaf_rn(p, f, SPECDEC_C3);
+  p = __fmaf_rn(p, f, SPECDEC_C2);
+  p = __fmaf_rn(p, f, SPECDEC_C1);
+  p = __fmaf_rn(p, f, 1.0f);
+  return __int_as_float(__float_as_int(p) + (int)((unsigned)i << 23));
+}
+// weight of logit z under (c, mc): exp2(z*c - m*c), one rounding in the exponent argument
+__device__ __forceinline__ float cweight(float z, float c, float mc) { return cexp2(__fmaf_rn(z, c, -mc)); }
+__device__ __forceinline__ u64 fix40(float x) { return __float2ull_rz(__fmul_rn(x, 1099511627776.0f)); }
+__device__ __forceinline__ u64 fix60(float x) { return __float2ull_rz(__fmul_rn(x, 1152921504606846976.0f)); }
+__device__ __forceinline__ unsigned u24_of(float u) {
+  if (!(u > 0.0f)) return 0u;
+  if (u >= 1.0f) return 16777215u;
+  return (unsigned)__fmul_rn(u, 16777216.0f);
+}
+// (S * u24) >> 24 with a 128-bit intermediate
+__device__ __forceinline__ u64 scale_u24(u64 S, unsigned u24) {
+  u64 hi = __umul64hi(S, (u64)u24), lo = S * (u64)u24;
+  return (hi << 40) | (lo >> 24);
+}
+// (S * q32) >> 32 with a 128-bit intermediate
+__device__ __forceinline__ u64 scale_q32(u64 S, u64 q32) {
+  u64 hi = __umul64hi(S, q32), lo = S * q32;
+  return (hi << 32) | (lo >> 32);
+}
+// order-preserving float -> uint32 key
+__device__ __forceinline__ unsigned fkey(float z) {
+  unsigned b = __float_as_uint(__fadd_rn(z, 0.0f));  // -0.0 -> +0.0 so that key order == float order
+  return b ^ ((b >> 31) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float fkey_inv(unsigned k) {
+  unsigned b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
+  return __uint_as_float(b);
+}
+
+// ---- Philox4x32-10, keyed by (seed; offset, global sequence id, lane) ----
+__device__ __forceinline__ unsigned philox_word0(u64 seed, u64 offset, unsigned seq, unsigned lane) {
+  unsigned c0 = (unsigned)offset, c1 = (unsigned)(offset >> 32), c2 = seq, c3 = lane;
+  unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    unsigned n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return c0;
+}
+__device__ __forceinline__ float philox_uniform(u64 seed, u64 offset, unsigned seq, unsigned lane) {
+  return __fmul_rn((float)(philox_word0(seed, offset, seq, lane) >> 8), 0x1p-24f);
+}
+
+// ---- 8-element vector access for the three logit dtypes ----
+// Vector v covers elements [8v, 8v+8).  `aligned` = row base 16-byte aligned (then every full
+// vector is one (bf16/f16) or two (f32) 16-byte loads).  Elements >= V read as -inf (weight 0).
+template <int DT> struct Elem;
+template <> struct Elem<DT_F32> { typedef float T; };
+template <> struct Elem<DT_BF16> { typedef __nv_bfloat16 T; };
+template <> struct Elem<DT_F16> { typedef __half T; };
+
+template <int DT>
+__device__ __forceinline__ float load1(const void* row, int j) {
+  if (DT == DT_F32) return __ldg((const float*)row + j);
+  if (DT == DT_BF16) return __uint_as_float(((unsigned)__ldg((const unsigned short*)row + j)) << 16);
+  return __half2float(__ushort_as_half(__ldg((const unsigned short*)row + j)));
+}
+
+template <int DT>
+__device__ __forceinline__ void load8(const void* row, int v, int V, bool aligned, float (&x)[8]) {
+  const int j0 = v * 8;
+  if (aligned && j0 + 8 <= V) {
+    if (DT == DT_F32) {
+      const float4* p = (const float4*)((const float*)row + j0);
+      float4 a = __ldg(p), b = __ldg(p + 1);
+      x[0] = a.x; x[1] = a.y; x[2] = a.z; x[3] = a.w; x[4] = b.x; x[5] = b.y; x[6] = b.z; x[7] = b.w;
+    } else {
+      uint4 a = __ldg((const uint4*)((const unsigned short*)row + j0));
+      unsigned w[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (DT == DT_BF16) {
+          x[2 * k] = __uint_as_float(w[k] << 16);
+          x[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+        } else {
+          __half2 h = *reinterpret_cast<__half2*>(&w[k]);
+          float2 f = __half22float2(h);
+          x[2 * k] = f.x; x[2 * k + 1] = f.y;
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) x[k] = (j0 + k < V) ? load1<DT>(row, j0 + k) : -INFINITY;
+  }
+}
+
+// ---- block-wide reductions for NT = 1024 threads (32 warps); `sh` = 33-entry scratch ----
+__device__ __forceinline__ u64 warp_sum_u64(u64 v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_min_f(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// All threads get the result.  Two barriers; safe to call back to back with the same scratch.
+__device__ __forceinline__ u64 block_sum_u64(u64 v, u64* sh) {
+  v = warp_sum_u64(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  u64 t = (lane < nw) ? sh[lane] : 0ull;
+  t = warp_sum_u64(t);
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ float block_max_f(float v, float* sh) {
+  v = warp_max_f(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? sh[lane] : -INFINITY;
+  t = warp_max_f(t);
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ float block_min_f(float v, float* sh) {
+  v = warp_min_f(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  float t = (lane < nw) ? sh[lane] : INFINITY;
+  t = warp_min_f(t);
+  __syncthreads();
+  return t;
+}
+__device__ __forceinline__ unsigned block_min_u32(unsigned v, unsigned* sh) {
+  v = __reduce_min_sync(0xffffffffu, v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  unsigned t = (lane < nw) ? sh[lane] : 0xFFFFFFFFu;
+  t = __reduce_min_sync(0xffffffffu, t);
+  __syncthreads();
+  return t;
+}
+
+}  // namespace specdec

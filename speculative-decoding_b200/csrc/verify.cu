@@ -1,0 +1,934 @@
+// verify.cu -- fused speculative-sampling verify for sm_100a (B200).
+//
+// Two kernels per verify step:
+//   rowstats_kernel : one CTA per (sequence, position, model) logit row.  Replaces
+//                     LogitsProcessor.__call__ (utils/logits_processor.py:13-15) incl. top-k (:59-63)
+//                     and nucleus (:73-81, :92-103) WITHOUT materialising probabilities: per row it
+//                     emits {max, 1/sum, cut value, cut index} (32 bytes).
+//   decide_kernel   : one CTA per sequence.  Accept test (sampling/speculative_decoding.py:139-145 or
+//                     engine/infer_engine.py:303-305), stop scan (:150-155), then ONE more sweep over
+//                     the single row (pair) that needs it: residual max(0,p-q) renormalisation +
+//                     inverse-CDF resample (:10-19,168,171) or the bonus row (:158-160).
+// All arithmetic is the canonical fp32/integer arithmetic of canon.cuh, so results are bit-exact
+// against the CPU oracle for every launch geometry.
+#include "canon.cuh"
+#include "../../include/specdec_b200.h"
+
+namespace specdec {
+
+constexpr int NT = 1024;       // threads per CTA (32 warps)
+constexpr int CAP = 8192;      // top-k / nucleus candidate capacity per row (shared memory)
+constexpr int MAXPART = 4096;  // warp-vector partial sums per row: V <= MAXPART*256
+constexpr size_t CAND_SMEM = (size_t)CAP * (sizeof(float) + sizeof(int) + sizeof(u64));
+
+struct RowOut {  // 32 bytes per logit row
+  float m, mc, inv, cut;
+  int jcut, flags;
+  u64 Sfix;
+};
+
+struct RowJob {
+  const void* tgt;
+  const void* drf;
+  long long tsb, tsg, dsb, dsg;  // element strides
+  int nT, nD;                    // target / draft rows per sequence
+  int V;
+  float c, c1;
+  int top_k;  // 0 = off
+  int use_p;
+  u64 tpq;  // floor(top_p * 2^32)
+  long long R;
+  RowOut* out;
+};
+
+template <int DT>
+__device__ __forceinline__ const void* row_ptr(const RowJob& job, long long r) {
+  const int rps = job.nT + job.nD;
+  const long long b = r / rps;
+  const int k = (int)(r - b * rps);
+  const size_t es = (DT == DT_F32) ? 4 : 2;
+  if (k < job.nT) return (const char*)job.tgt + (size_t)(b * job.tsb + (long long)k * job.tsg) * es;
+  return (const char*)job.drf + (size_t)(b * job.dsb + (long long)(k - job.nT) * job.dsg) * es;
+}
+
+// Visit every 8-element vector of a row: f(x[8], j0).  4 independent vector loads in flight.
+template <int DT, typename F>
+__device__ __forceinline__ void sweep(const void* row, int V, bool aligned, F f) {
+  const int NV = (V + 7) >> 3;
+  int v = threadIdx.x;
+  for (; v + 3 * NT < NV; v += 4 * NT) {
+    float x0[8], x1[8], x2[8], x3[8];
+    load8<DT>(row, v, V, aligned, x0);
+    load8<DT>(row, v + NT, V, aligned, x1);
+    load8<DT>(row, v + 2 * NT, V, aligned, x2);
+    load8<DT>(row, v + 3 * NT, V, aligned, x3);
+    f(x0, v * 8);
+    f(x1, (v + NT) * 8);
+    f(x2, (v + 2 * NT) * 8);
+    f(x3, (v + 3 * NT) * 8);
+  }
+  for (; v < NV; v += NT) {
+    float x[8];
+    load8<DT>(row, v, V, aligned, x);
+    f(x, v * 8);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// top-k / nucleus cut selection, generic over the element source (candidate list or full row)
+// ---------------------------------------------------------------------------------------------
+struct CandSrc {
+  float* cz;
+  int* cj;
+  u64* cw;
+  int n;
+  float c1, mc1;
+  __device__ void prepare(unsigned kthkey) const {  // T=1 masses of the top-k-kept candidates
+    for (int i = threadIdx.x; i < n; i += NT) cw[i] = (fkey(cz[i]) >= kthkey) ? fix40(cweight(cz[i], c1, mc1)) : 0ull;
+    __syncthreads();
+  }
+  template <typename F>
+  __device__ void each(unsigned, bool, F f) const {
+    for (int i = threadIdx.x; i < n; i += NT) f(cz[i], fkey(cz[i]), cj[i], cw[i]);
+  }
+};
+template <int DT>
+struct RowSrc {
+  const void* row;
+  int V;
+  bool aligned;
+  float c1, mc1;
+  __device__ void prepare(unsigned) const {}
+  template <typename F>
+  __device__ void each(unsigned kthkey, bool need_w, F f) const {
+    sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (j0 + k < V) {
+          const unsigned key = fkey(x[k]);
+          const u64 w = (need_w && key >= kthkey) ? fix40(cweight(x[k], c1, mc1)) : 0ull;
+          f(x[k], key, j0 + k, w);
+        }
+    });
+  }
+};
+
+// Finds (cut, jcut, Sfix) for the masked modes.  S1_full: T=1 mass of the whole row (pure nucleus
+// only; with top-k it is recomputed over the kept set).  Block-uniform control flow.
+template <typename Src>
+__device__ void select_cut(const Src& src, int V, int top_k, int use_p, u64 tpq, u64 S1_full, float c, float mc,
+                           u64* sh64, unsigned* shu, float& cut_out, int& jcut_out, u64& Sfix_out) {
+  unsigned kthkey = 0;
+  if (top_k > 0) {  // largest key K with count(key >= K) >= top_k   (utils/logits_processor.py:61)
+    unsigned K = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned tr = K | (1u << bit);
+      u64 cnt = 0;
+      src.each(0u, false, [&](float, unsigned key, int, u64) { cnt += (key >= tr) ? 1u : 0u; });
+      cnt = block_sum_u64(cnt, sh64);
+      if (cnt >= (u64)top_k) K = tr;
+    }
+    kthkey = K;
+  }
+  src.prepare(kthkey);
+  unsigned cutkey = kthkey;
+  int jcut = V;
+  if (use_p) {
+    u64 S1 = S1_full;
+    if (top_k > 0) {
+      u64 loc = 0;
+      src.each(kthkey, true, [&](float, unsigned, int, u64 w) { loc += w; });
+      S1 = block_sum_u64(loc, sh64);
+    }
+    const u64 thr = scale_q32(S1, tpq);
+    // v' = max key whose strictly-greater mass still exceeds thr
+    unsigned vp = 0;
+    for (int bit = 31; bit >= 0; --bit) {
+      const unsigned tr = vp | (1u << bit);
+      u64 loc = 0;
+      src.each(kthkey, true, [&](float, unsigned key, int, u64 w) { loc += (key > tr) ? w : 0ull; });
+      const u64 G = block_sum_u64(loc, sh64);
+      if (G > thr) vp = tr;
+    }
+    unsigned lk = 0xFFFFFFFFu;
+    u64 locG = 0;
+    src.each(kthkey, false, [&](float, unsigned key, int, u64) {
+      if (key > vp && key >= kthkey) lk = min(lk, key);
+    });
+    cutkey = block_min_u32(lk, shu);
+    u64 cntc = 0;
+    src.each(kthkey, true, [&](float, unsigned key, int, u64 w) {
+      locG += (key > cutkey) ? w : 0ull;
+      cntc += (key == cutkey) ? 1u : 0u;
+    });
+    const u64 Gc = block_sum_u64(locG, sh64);
+    cntc = block_sum_u64(cntc, sh64);
+    const u64 wc = fix40(cweight(fkey_inv(cutkey), src.c1, src.mc1));
+    u64 mkeep = cntc;
+    if (wc > 0 && thr >= Gc) {
+      const u64 q = (thr - Gc) / wc + 1ull;
+      mkeep = q < cntc ? q : cntc;
+    }
+    if (mkeep < cntc) {  // keep the first mkeep ties in ascending index order
+      int lo = 0, hi = V - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        u64 cnt = 0;
+        src.each(kthkey, false, [&](float, unsigned key, int j, u64) { cnt += (key == cutkey && j <= mid) ? 1u : 0u; });
+        cnt = block_sum_u64(cnt, sh64);
+        if (cnt >= mkeep) hi = mid; else lo = mid + 1;
+      }
+      jcut = lo;
+    }
+  }
+  u64 loc = 0;
+  src.each(0u, false, [&](float z, unsigned key, int j, u64) {
+    if (key > cutkey || (key == cutkey && j <= jcut)) loc += fix40(cweight(z, c, mc));
+  });
+  Sfix_out = block_sum_u64(loc, sh64);
+  cut_out = fkey_inv(cutkey);
+  jcut_out = jcut;
+}
+
+// ---------------------------------------------------------------------------------------------
+// rowstats_kernel
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ unsigned shu[33];
+  __shared__ int s_count;
+  const int V = job.V;
+  const float c = job.c;
+  const bool masked = (job.top_k > 0) || job.use_p;
+  for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+    const void* row = row_ptr<DT>(job, r);
+    const bool aligned = (((size_t)row) & 15) == 0;
+    // sweep 1: row max (+ per-thread maxima, reused as candidate thresholds)
+    float tmax = -INFINITY;
+    sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tmax = fmaxf(tmax, x[k]);
+    });
+    const float m = block_max_f(tmax, shf);
+    const float mc = __fmul_rn(m, c);
+    float cut = -INFINITY;
+    int jcut = V;
+    u64 Sfix = 0;
+    if (!masked) {
+      u64 s = 0;
+      sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) s += fix40(cweight(x[k], c, mc));
+      });
+      Sfix = block_sum_u64(s, sh64);
+    } else {
+      const float c1 = job.c1;
+      const float mc1 = __fmul_rn(m, c1);
+      // thresholds guaranteeing >= 32 / 128 / 512 / 1024 elements above them
+      float pm = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+      float qm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 2));
+      qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
+      float wm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 8));
+      wm = fmaxf(wm, __shfl_xor_sync(0xffffffffu, wm, 16));
+      float tau[4];
+      tau[0] = block_min_f(wm, shf);
+      tau[1] = block_min_f(qm, shf);
+      tau[2] = block_min_f(pm, shf);
+      tau[3] = block_min_f(tmax, shf);
+      int L = -1;
+      u64 S1 = 0;
+      if (job.top_k > 0) {
+        L = job.top_k <= 32 ? 0 : job.top_k <= 128 ? 1 : job.top_k <= 512 ? 2 : job.top_k <= 1024 ? 3 : -1;
+      } else {
+        // pure nucleus: exact T=1 mass of the row and of the four nested candidate sets
+        u64 sa = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+        unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+        const float t0 = tau[0], t1 = tau[1], t2 = tau[2], t3 = tau[3];
+        sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const u64 w = fix40(cweight(x[k], c1, mc1));
+            sa += w;
+            if (x[k] >= t3 && j0 + k < V) {
+              m3 += w; ++n3;
+              if (x[k] >= t2) {
+                m2 += w; ++n2;
+                if (x[k] >= t1) {
+                  m1 += w; ++n1;
+                  if (x[k] >= t0) { m0 += w; ++n0; }
+                }
+              }
+            }
+          }
+        });
+        S1 = block_sum_u64(sa, sh64);
+        const u64 M[4] = {block_sum_u64(m0, sh64), block_sum_u64(m1, sh64), block_sum_u64(m2, sh64),
+                          block_sum_u64(m3, sh64)};
+        const u64 N[4] = {block_sum_u64(n0, sh64), block_sum_u64(n1, sh64), block_sum_u64(n2, sh64),
+                          block_sum_u64(n3, sh64)};
+        const u64 thr = scale_q32(S1, job.tpq);
+#pragma unroll
+        for (int l = 3; l >= 0; --l)
+          if (M[l] > thr && N[l] <= (u64)CAP) L = l;
+      }
+      float* cz = (float*)dyn_smem;
+      int* cj = (int*)(dyn_smem + (size_t)CAP * 4);
+      u64* cw = (u64*)(dyn_smem + (size_t)CAP * 8);
+      int n = 0;
+      if (L >= 0) {
+        const float th = tau[L];
+        if (threadIdx.x == 0) s_count = 0;
+        __syncthreads();
+        sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)
+            if (x[k] >= th && j0 + k < V) {
+              const int slot = atomicAdd(&s_count, 1);
+              if (slot < CAP) { cz[slot] = x[k]; cj[slot] = j0 + k; }
+            }
+        });
+        __syncthreads();
+        n = s_count;
+        __syncthreads();
+        if (n > CAP || n < job.top_k) L = -1;
+      }
+      if (L >= 0) {
+        CandSrc src{cz, cj, cw, n, c1, mc1};
+        select_cut(src, V, job.top_k, job.use_p, job.tpq, S1, c, mc, sh64, shu, cut, jcut, Sfix);
+      } else {  // exact but slow: every selection step is a sweep over the row
+        RowSrc<DT> src{row, V, aligned, c1, mc1};
+        if (job.use_p && job.top_k == 0 && S1 == 0) {
+          u64 sa = 0;
+          src.each(0u, true, [&](float, unsigned, int, u64 w) { sa += w; });
+          S1 = block_sum_u64(sa, sh64);
+        }
+        select_cut(src, V, job.top_k, job.use_p, job.tpq, S1, c, mc, sh64, shu, cut, jcut, Sfix);
+      }
+    }
+    if (threadIdx.x == 0) {
+      RowOut o;
+      o.m = m; o.mc = mc;
+      const float S32 = __fmul_rn(__ull2float_rn(Sfix), 0x1p-40f);
+      o.inv = __fdiv_rn(1.0f, S32);
+      o.cut = cut; o.jcut = jcut; o.flags = 0; o.Sfix = Sfix;
+      job.out[r] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sampling helpers (block-wide)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ bool kept(const RowOut& ro, float z, int j) {
+  return z > ro.cut || (z == ro.cut && j <= ro.jcut);
+}
+template <int DT>
+__device__ __forceinline__ float row_prob(const RowOut& ro, const void* row, int j, float c) {
+  const float z = load1<DT>(row, j);
+  const float e = kept(ro, z, j) ? cweight(z, c, ro.mc) : 0.0f;
+  return __fmul_rn(e, ro.inv);
+}
+
+// Inverse CDF over integer weights wf(v, w[8]) in index order: returns the first index whose
+// inclusive prefix sum exceeds target.  part[] receives the per-256-element partial sums.
+// total_out = sum of all weights.  If target >= total the result is -1.
+template <typename WF>
+__device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in, unsigned u24, u64* part, u64* sh64,
+                                  long long* s_res, u64& total_out) {
+  const int NV = (V + 7) >> 3;
+  const int P = (NV + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += NT) {  // warp-uniform
+    const int v = base + lane;
+    u64 s = 0;
+    if (v < NV) {
+      u64 w[8];
+      wf(v, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += w[k];
+    }
+    s = warp_sum_u64(s);
+    if (lane == 0) part[base >> 5] = s;
+  }
+  __syncthreads();
+  u64 loc = 0;
+  for (int i = threadIdx.x; i < P; i += NT) loc += part[i];
+  const u64 total = block_sum_u64(loc, sh64);
+  total_out = total;
+  const u64 target = have_target ? target_in : scale_u24(total, u24);
+  if (threadIdx.x < 32) {
+    long long res = -1;
+    if (target < total) {
+      // lane owns a contiguous chunk of partials
+      const int per = (P + 31) >> 5;
+      const int i0 = lane * per, i1 = min(P, i0 + per);
+      u64 cs = 0;
+      for (int i = i0; i < i1; ++i) cs += part[i];
+      u64 incl = cs;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, incl > target);
+      const int owner = __ffs(bal) - 1;
+      int seg = 0;
+      u64 before = 0;
+      if (lane == owner) {
+        u64 run = incl - cs;
+        int i = i0;
+        for (; i < i1; ++i) {
+          if (run + part[i] > target) break;
+          run += part[i];
+        }
+        seg = i; before = run;
+      }
+      seg = __shfl_sync(0xffffffffu, seg, owner);
+      before = __shfl_sync(0xffffffffu, before, owner);
+      // evaluate the 256 elements of that segment
+      const int v = seg * 32 + lane;
+      u64 w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = 0;
+      if (v < NV) wf(v, w);
+      u64 ls = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ls += w[k];
+      u64 li = ls;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const u64 t = __shfl_up_sync(0xffffffffu, li, o);
+        if (lane >= o) li += t;
+      }
+      const u64 loc_t = target - before;
+      const unsigned b2 = __ballot_sync(0xffffffffu, li > loc_t);
+      const int own2 = __ffs(b2) - 1;
+      if (lane == own2) {
+        u64 run = li - ls;
+        int k = 0;
+#pragma unroll
+        for (; k < 8; ++k) {
+          if (run + w[k] > loc_t) break;
+          run += w[k];
+        }
+        res = (long long)v * 8 + k;
+      }
+      res = __shfl_sync(0xffffffffu, res, own2 < 0 ? 0 : own2);
+    }
+    if (lane == 0) *s_res = res;
+  }
+  __syncthreads();
+  const long long out = *s_res;
+  __syncthreads();
+  return out;
+}
+
+// block-wide argmax, first index on ties; value must be >= 0; returns -1 if no value > floor_excl
+__device__ long long block_argmax(float best, int idx, float* shf, int* shi, long long* s_res) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) { shf[w] = best; shi[w] = idx; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = shf[lane]; idx = shi[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (lane == 0) *s_res = (idx == 0x7FFFFFFF) ? -1ll : (long long)idx;
+  }
+  __syncthreads();
+  const long long out = *s_res;
+  __syncthreads();
+  return out;
+}
+
+struct Scratch {
+  u64* part;
+  u64* sh64;
+  float* shf;
+  int* shi;
+  long long* s_res;
+};
+
+// sample() on a processed target row (utils/logits_processor.py:36 greedy / inverse CDF)
+template <int DT>
+__device__ long long sample_p_row(const void* row, const RowOut& ro, int V, float c, bool greedy, float u,
+                                  const Scratch& sc) {
+  const bool aligned = (((size_t)row) & 15) == 0;
+  if (greedy) {
+    float best = -1.0f;
+    int idx = 0x7FFFFFFF;
+    sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (j0 + k < V) {
+          const float e = kept(ro, x[k], j0 + k) ? cweight(x[k], c, ro.mc) : 0.0f;
+          if (e > best) { best = e; idx = j0 + k; }
+        }
+    });
+    return block_argmax(best, idx, sc.shf, sc.shi, sc.s_res);
+  }
+  u64 total;
+  auto wf = [&](int v, u64(&w)[8]) {
+    float x[8];
+    load8<DT>(row, v, V, aligned, x);
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      w[k] = (v * 8 + k < V && kept(ro, x[k], v * 8 + k)) ? fix40(cweight(x[k], c, ro.mc)) : 0ull;
+  };
+  return invcdf_sweep(V, wf, true, scale_u24(ro.Sfix, u24_of(u)), 0u, sc.part, sc.sh64, sc.s_res, total);
+}
+
+// max_fn(p - q) then sample (sampling/speculative_decoding.py:10-19,168,171); -1 => caller falls back to p
+template <int DT>
+__device__ long long sample_residual(const void* prow, const RowOut& rp, const void* qrow, const RowOut& rq, int V,
+                                     float c, bool greedy, float u, u64 rmin, const Scratch& sc) {
+  const bool pal = (((size_t)prow) & 15) == 0, qal = (((size_t)qrow) & 15) == 0;
+  auto resid = [&](float zp, float zq, int j) -> float {
+    const float P = __fmul_rn(kept(rp, zp, j) ? cweight(zp, c, rp.mc) : 0.0f, rp.inv);
+    const float Q = __fmul_rn(kept(rq, zq, j) ? cweight(zq, c, rq.mc) : 0.0f, rq.inv);
+    const float r = __fsub_rn(P, Q);
+    return r > 0.0f ? r : 0.0f;
+  };
+  u64 total;
+  float best = 0.0f;
+  int idx = 0x7FFFFFFF;
+  auto wf = [&](int v, u64(&w)[8]) {
+    float xp[8], xq[8];
+    load8<DT>(prow, v, V, pal, xp);
+    load8<DT>(qrow, v, V, qal, xq);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = v * 8 + k;
+      const float r = (j < V) ? resid(xp[k], xq[k], j) : 0.0f;
+      w[k] = fix60(r);
+      if (r > best || (r == best && r > 0.0f && j < idx)) { best = r; idx = j; }
+    }
+  };
+  // u24 path: target depends on the total, which the sweep itself produces
+  long long x = invcdf_sweep(V, wf, false, 0ull, u24_of(u), sc.part, sc.sh64, sc.s_res, total);
+  if (total <= rmin) return -1;
+  if (greedy) {
+    const long long g = block_argmax(best, idx, sc.shf, sc.shi, sc.s_res);
+    return g;
+  }
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decide_kernel: one CTA per sequence
+// ---------------------------------------------------------------------------------------------
+struct DecideJob {
+  RowJob rj;
+  const long long* draft_tokens;
+  const float* u_accept;
+  const float* u_sample;
+  u64 seed, offset;
+  long long seq0;
+  int gamma;
+  int greedy;
+  int flags;
+  const long long* stop;
+  int n_stop;
+  int* n_acc;
+  long long* next_tok;
+  unsigned char* mask;
+  float* p_tok;
+  float* q_tok;
+  int* first_stop;
+  float* next_prob;
+  int* packed;
+  int lane_sample;  // philox lane of the sample stream
+};
+
+template <int DT>
+__global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
+  __shared__ u64 part[MAXPART];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ int shi[33];
+  __shared__ long long s_res;
+  __shared__ int s_acc[64];
+  __shared__ int s_n;
+  const Scratch sc{part, sh64, shf, shi, &s_res};
+  const RowJob& rj = job.rj;
+  const int b = blockIdx.x, g = job.gamma, V = rj.V;
+  const int rps = rj.nT + rj.nD;
+  const float c = rj.c;
+  const bool greedy = job.greedy != 0;
+  const bool ngram = (job.flags & SPECDEC_NGRAM) != 0;
+  const RowOut* ro = rj.out + (long long)b * rps;
+  const unsigned seq = (unsigned)(job.seq0 + b);
+  const long long* toks = job.draft_tokens + (long long)b * g;
+
+  // 1. per-position accept test
+  if (ngram) {
+    for (int i = 0; i < g; ++i) {  // accept iff draft == sample(p_i)  (ngram_assisted.py:114-119)
+      const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job.offset, seq, i);
+      const void* prow = row_ptr<DT>(rj, (long long)b * rps + i);
+      const long long s = sample_p_row<DT>(prow, ro[i], V, c, greedy, u, sc);
+      if (threadIdx.x == 0) {
+        const int tok = (int)min(max(toks[i], 0ll), (long long)V - 1);
+        s_acc[i] = (s == toks[i]);
+        job.p_tok[(long long)b * g + i] = row_prob<DT>(ro[i], prow, tok, c);
+        job.q_tok[(long long)b * g + i] = 0.0f;
+      }
+    }
+  } else if (threadIdx.x < g) {
+    const int i = threadIdx.x;
+    const int tok = (int)min(max(toks[i], 0ll), (long long)V - 1);  // ids outside [0,V) are clamped
+    const void* prow = row_ptr<DT>(rj, (long long)b * rps + i);
+    const void* qrow = row_ptr<DT>(rj, (long long)b * rps + rj.nT + i);
+    const float p = row_prob<DT>(ro[i], prow, tok, c);
+    const float q = row_prob<DT>(ro[rj.nT + i], qrow, tok, c);
+    const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job.offset, seq, i);
+    int acc;
+    if (job.flags & SPECDEC_ACCEPT_BATCHED) {  // engine/infer_engine.py:303-305 (python floats = double)
+      const double ap = (q <= 0.0f) ? 1.0 : fmin(1.0, (double)p / (double)q);
+      acc = ((double)u < ap);
+    } else {  // sampling/speculative_decoding.py:143 : reject iff r > p/q  (NaN => accept)
+      const float frac = __fdiv_rn(p, q);
+      acc = !(u > frac);
+    }
+    s_acc[i] = acc;
+    job.p_tok[(long long)b * g + i] = p;
+    job.q_tok[(long long)b * g + i] = q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int n = g;
+    for (int i = 0; i < g; ++i) {
+      job.mask[(long long)b * g + i] = (unsigned char)s_acc[i];
+      if (!s_acc[i] && n == g) n = i;
+    }
+    int fs = -1;
+    for (int i = 0; i < n && fs < 0; ++i)
+      for (int k = 0; k < job.n_stop; ++k)
+        if (toks[i] == job.stop[k]) { fs = i; break; }
+    job.n_acc[b] = n;
+    job.first_stop[b] = fs;
+    s_n = n;
+  }
+  __syncthreads();
+  const int n = s_n;
+
+  // 2. next token
+  const float us = job.u_sample ? job.u_sample[b] : philox_uniform(job.seed, job.offset, seq, (unsigned)job.lane_sample);
+  long long x = -1;
+  int prow_idx = -1;  // target row x was drawn from (for next_prob)
+  if (n == g) {
+    if (!(job.flags & SPECDEC_NO_BONUS)) {
+      prow_idx = g;
+      x = sample_p_row<DT>(row_ptr<DT>(rj, (long long)b * rps + g), ro[g], V, c, greedy, us, sc);
+    }
+  } else {
+    const void* prow = row_ptr<DT>(rj, (long long)b * rps + n);
+    if (ngram || (job.flags & SPECDEC_SKIP_ADJUST)) {
+      prow_idx = n;
+      x = sample_p_row<DT>(prow, ro[n], V, c, greedy, us, sc);
+    } else {
+      const void* qrow = row_ptr<DT>(rj, (long long)b * rps + rj.nT + n);
+      const u64 rmin = (job.flags & SPECDEC_RESID_FALLBACK) ? 1152921ull : 0ull;
+      x = sample_residual<DT>(prow, ro[n], qrow, ro[rj.nT + n], V, c, greedy, us, rmin, sc);
+      if (x < 0) {
+        prow_idx = n;
+        x = sample_p_row<DT>(prow, ro[n], V, c, greedy, us, sc);
+      }
+    }
+  }
+  if (threadIdx.x == 0) {
+    job.next_tok[b] = x;
+    if (job.next_prob)
+      job.next_prob[b] = (prow_idx >= 0 && x >= 0)
+                             ? row_prob<DT>(ro[prow_idx], row_ptr<DT>(rj, (long long)b * rps + prow_idx), (int)x, c)
+                             : 0.0f;
+    if (job.packed) {
+      int* pk = job.packed + (long long)b * (g + 2);
+      pk[0] = n;
+      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
+      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
+      pk[1 + n] = (int)x;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// probabilities materialised (LogitsProcessor.__call__), sample() on given probs, philox dump
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(NT, 1) probs_kernel(RowJob job, float* probs, float* stats) {
+  for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+    const void* row = row_ptr<DT>(job, r);
+    const bool aligned = (((size_t)row) & 15) == 0;
+    const RowOut ro = job.out[r];
+    float* out = probs ? probs + (size_t)r * job.V : nullptr;
+    if (out)
+      sweep<DT>(row, job.V, aligned, [&](const float(&x)[8], int j0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (j0 + k < job.V)
+            out[j0 + k] = __fmul_rn(kept(ro, x[k], j0 + k) ? cweight(x[k], job.c, ro.mc) : 0.0f, ro.inv);
+      });
+    if (stats && threadIdx.x == 0) {
+      float* s = stats + r * 8;
+      s[0] = ro.m; s[1] = __fmul_rn(__ull2float_rn(ro.Sfix), 0x1p-40f); s[2] = ro.inv; s[3] = ro.cut;
+      s[4] = (float)ro.jcut; s[5] = 0; s[6] = 0; s[7] = 0;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NT, 1) sample_probs_kernel(const float* probs, long long rows, int V, int greedy,
+                                                             const float* u, long long* tok) {
+  __shared__ u64 part[MAXPART];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ int shi[33];
+  __shared__ long long s_res;
+  for (long long r = blockIdx.x; r < rows; r += gridDim.x) {
+    const float* row = probs + (size_t)r * V;
+    const bool aligned = (((size_t)row) & 15) == 0;
+    long long x;
+    if (greedy) {
+      float best = -INFINITY;
+      int idx = 0x7FFFFFFF;
+      sweep<DT_F32>(row, V, aligned, [&](const float(&p)[8], int j0) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (j0 + k < V && p[k] > best) { best = p[k]; idx = j0 + k; }
+      });
+      x = block_argmax(best, idx, shf, shi, &s_res);
+      if (x < 0) x = 0;
+    } else {
+      u64 total;
+      auto wf = [&](int v, u64(&w)[8]) {
+        float p[8];
+        load8<DT_F32>(row, v, V, aligned, p);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) w[k] = (v * 8 + k < V && p[k] > 0.0f) ? fix40(p[k]) : 0ull;
+      };
+      x = invcdf_sweep(V, wf, false, 0ull, u24_of(u[r]), part, sh64, &s_res, total);
+      if (x < 0) x = 0;
+    }
+    if (threadIdx.x == 0) tok[r] = x;
+  }
+}
+
+__global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g, float* ua, float* us) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= B * (g + 1)) return;
+  const int b = t / (g + 1), i = t % (g + 1);
+  const unsigned seq = (unsigned)(seq0 + b);
+  if (i < g) { if (ua) ua[(long long)b * g + i] = philox_uniform(seed, offset, seq, (unsigned)i); }
+  else if (us) us[b] = philox_uniform(seed, offset, seq, 0x10000u);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
+static int g_sms = 0;
+static int num_sms() {
+  if (g_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_sms <= 0) g_sms = 148;
+  }
+  return g_sms;
+}
+
+static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long tsb, long long tsg, long long dsb,
+                       long long dsg, int nT, int nD, int V, float temperature, int top_k, float top_p, long long R,
+                       void* workspace, size_t workspace_bytes) {
+  if (V <= 0 || V > MAXPART * 256 || !(temperature > 0.0f) || R < 0) return SPECDEC_ERR_RANGE;
+  if (workspace_bytes < (size_t)R * sizeof(RowOut) || (R > 0 && !workspace)) return SPECDEC_ERR_WORKSPACE;
+  rj.tgt = tgt; rj.drf = drf; rj.tsb = tsb; rj.tsg = tsg; rj.dsb = dsb; rj.dsg = dsg;
+  rj.nT = nT; rj.nD = nD; rj.V = V;
+  rj.c = (float)(1.4426950408889634 / (double)temperature);
+  rj.c1 = (float)1.4426950408889634;
+  rj.top_k = (top_k > 0 && top_k < V) ? top_k : 0;
+  rj.use_p = (top_p > 0.0f && top_p < 1.0f) ? 1 : 0;
+  rj.tpq = rj.use_p ? (u64)((double)top_p * 4294967296.0) : 0ull;
+  rj.R = R;
+  rj.out = (RowOut*)workspace;
+  return 0;
+}
+
+template <int DT>
+static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
+  if (rj.R == 0) return cudaSuccess;
+  const bool masked = rj.top_k > 0 || rj.use_p;
+  const size_t smem = masked ? CAND_SMEM : 0;
+  if (masked) {
+    cudaError_t e = cudaFuncSetAttribute(rowstats_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  const int grid = (int)(rj.R < (long long)num_sms() ? rj.R : (long long)num_sms());
+  rowstats_kernel<DT><<<grid, NT, smem, st>>>(rj);
+  return cudaGetLastError();
+}
+
+#define DISPATCH_DT(dtype, ...)                                          \
+  switch (dtype) {                                                       \
+    case SPECDEC_F32: { constexpr int DT = DT_F32; __VA_ARGS__; } break;   \
+    case SPECDEC_BF16: { constexpr int DT = DT_BF16; __VA_ARGS__; } break; \
+    case SPECDEC_F16: { constexpr int DT = DT_F16; __VA_ARGS__; } break;   \
+    default: return SPECDEC_ERR_DTYPE;                                   \
+  }
+
+}  // namespace specdec
+
+using namespace specdec;
+
+extern "C" {
+
+int specdec_version(void) { return 100; }
+
+const char* specdec_error_string(int code) {
+  switch (code) {
+    case 0: return "ok";
+    case SPECDEC_ERR_ARG: return "invalid argument";
+    case SPECDEC_ERR_WORKSPACE: return "workspace too small";
+    case SPECDEC_ERR_DTYPE: return "unsupported dtype";
+    case SPECDEC_ERR_RANGE: return "value out of supported range";
+    default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+  }
+}
+
+size_t specdec_workspace_bytes(int64_t rows) { return (size_t)(rows < 0 ? 0 : rows) * (sizeof(RowOut) + 16) + 256; }
+
+int specdec_verify(const void* target_logits, const void* draft_logits, int dtype, const int64_t* draft_tokens,
+                   const float* u_accept, const float* u_sample, uint64_t philox_seed, uint64_t philox_offset,
+                   int64_t seq_id0, int B, int gamma, int V, int64_t stride_tb, int64_t stride_tg, int64_t stride_db,
+                   int64_t stride_dg, float temperature, int top_k, float top_p, int sample_mode, int flags,
+                   const int64_t* stop_tokens, int n_stop, int32_t* n_accepted, int64_t* next_token,
+                   uint8_t* accept_mask, float* p_tok, float* q_tok, int32_t* first_stop, float* next_prob,
+                   int32_t* packed, void* workspace, size_t workspace_bytes, specdec_stream_t stream) {
+  if (B < 0 || gamma < 0 || gamma > 64 || !target_logits) return SPECDEC_ERR_ARG;
+  if (B == 0) return 0;
+  const bool ngram = flags & SPECDEC_NGRAM;
+  if (!ngram && gamma > 0 && !draft_logits) return SPECDEC_ERR_ARG;
+  if (gamma > 0 && (!draft_tokens || !accept_mask || !p_tok || !q_tok)) return SPECDEC_ERR_ARG;
+  if (!n_accepted || !next_token || !first_stop) return SPECDEC_ERR_ARG;
+  if (n_stop > 0 && !stop_tokens) return SPECDEC_ERR_ARG;
+  if (sample_mode != SPECDEC_SAMPLE_GREEDY && sample_mode != SPECDEC_SAMPLE_INVCDF) return SPECDEC_ERR_ARG;
+  const int nT = gamma + ((flags & SPECDEC_NO_BONUS) ? 0 : 1);
+  const int nD = ngram ? 0 : gamma;
+  if (nT + nD == 0) return SPECDEC_ERR_ARG;
+  DecideJob dj;
+  int rc = fill_rowjob(dj.rj, target_logits, draft_logits, stride_tb, stride_tg, stride_db, stride_dg, nT, nD, V,
+                       temperature, top_k, top_p, (long long)B * (nT + nD), workspace, workspace_bytes);
+  if (rc) return rc;
+  dj.draft_tokens = (const long long*)draft_tokens; dj.u_accept = u_accept; dj.u_sample = u_sample;
+  dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = gamma;
+  dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = flags;
+  dj.stop = (const long long*)stop_tokens; dj.n_stop = n_stop;
+  dj.n_acc = n_accepted; dj.next_tok = (long long*)next_token; dj.mask = accept_mask; dj.p_tok = p_tok;
+  dj.q_tok = q_tok; dj.first_stop = first_stop; dj.next_prob = next_prob; dj.packed = packed;
+  dj.lane_sample = 0x10000;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+  DISPATCH_DT(dtype, {
+    cudaError_t e = launch_rowstats<DT>(dj.rj, st);
+    if (e != cudaSuccess) return (int)e;
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    decide_kernel<DT><<<B, NT, 0, st>>>(dj);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  });
+  if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+  return 0;
+}
+
+int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {
+  g_ev[0] = (cudaEvent_t)ev_start; g_ev[1] = (cudaEvent_t)ev_mid; g_ev[2] = (cudaEvent_t)ev_end;
+  return 0;
+}
+
+int specdec_process_probs(const void* logits, int dtype, int64_t rows, int V, int64_t stride, float temperature,
+                          int top_k, float top_p, float* probs, float* row_stats, void* workspace,
+                          size_t workspace_bytes, specdec_stream_t stream) {
+  if (rows < 0 || !logits) return SPECDEC_ERR_ARG;
+  if (rows == 0) return 0;
+  RowJob rj;
+  int rc = fill_rowjob(rj, logits, nullptr, stride, 0, 0, 0, 1, 0, V, temperature, top_k, top_p, rows, workspace,
+                       workspace_bytes);
+  if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, {
+    cudaError_t e = launch_rowstats<DT>(rj, st);
+    if (e != cudaSuccess) return (int)e;
+    const int grid = (int)(rows < 4LL * num_sms() ? rows : 4LL * num_sms());
+    probs_kernel<DT><<<grid, NT, 0, st>>>(rj, probs, row_stats);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  });
+  return 0;
+}
+
+int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int64_t stride, float temperature,
+                        int top_k, float top_p, int sample_mode, const float* u, uint64_t philox_seed,
+                        uint64_t philox_offset, int64_t seq_id0, int lane_id, int64_t* tok, float* ptok,
+                        void* workspace, size_t workspace_bytes, specdec_stream_t stream) {
+  if (rows < 0 || !logits || !tok) return SPECDEC_ERR_ARG;
+  if (rows == 0) return 0;
+  if (rows > 0x7fffffff) return SPECDEC_ERR_RANGE;
+  if (sample_mode != SPECDEC_SAMPLE_GREEDY && sample_mode != SPECDEC_SAMPLE_INVCDF) return SPECDEC_ERR_ARG;
+  // a verify step with gamma = 0: every sequence "accepts all" and draws its bonus token
+  const size_t need = (size_t)rows * sizeof(RowOut) + (size_t)rows * (sizeof(int) * 2);
+  if (workspace_bytes < need) return SPECDEC_ERR_WORKSPACE;
+  DecideJob dj;
+  int rc = fill_rowjob(dj.rj, logits, nullptr, stride, 0, 0, 0, 1, 0, V, temperature, top_k, top_p, rows, workspace,
+                       workspace_bytes);
+  if (rc) return rc;
+  int* scratch = (int*)((char*)workspace + (size_t)rows * sizeof(RowOut));
+  dj.draft_tokens = nullptr; dj.u_accept = nullptr; dj.u_sample = u;
+  dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = 0;
+  dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = 0; dj.stop = nullptr; dj.n_stop = 0;
+  dj.n_acc = scratch; dj.first_stop = scratch + rows; dj.next_tok = (long long*)tok; dj.mask = nullptr;
+  dj.p_tok = nullptr; dj.q_tok = nullptr; dj.next_prob = ptok; dj.packed = nullptr;
+  dj.lane_sample = 0x20000 + lane_id;
+  cudaStream_t st = (cudaStream_t)stream;
+  DISPATCH_DT(dtype, {
+    cudaError_t e = launch_rowstats<DT>(dj.rj, st);
+    if (e != cudaSuccess) return (int)e;
+    decide_kernel<DT><<<(int)rows, NT, 0, st>>>(dj);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return (int)e;
+  });
+  return 0;
+}
+
+int specdec_sample_probs(const float* probs, int64_t rows, int V, int sample_mode, const float* u, int64_t* tok,
+                         specdec_stream_t stream) {
+  if (rows < 0 || !probs || !tok) return SPECDEC_ERR_ARG;
+  if (rows == 0) return 0;
+  if (V <= 0 || V > MAXPART * 256) return SPECDEC_ERR_RANGE;
+  const int greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY);
+  if (!greedy && !u) return SPECDEC_ERR_ARG;
+  const int grid = (int)(rows < 4LL * num_sms() ? rows : 4LL * num_sms());
+  sample_probs_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(probs, rows, V, greedy, u, (long long*)tok);
+  return (int)cudaGetLastError();
+}
+
+int specdec_philox_uniform(uint64_t seed, uint64_t offset, int64_t seq_id0, int B, int gamma, float* u_accept,
+                           float* u_sample, specdec_stream_t stream) {
+  if (B < 0 || gamma < 0) return SPECDEC_ERR_ARG;
+  const int n = B * (gamma + 1);
+  if (n == 0) return 0;
+  philox_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(seed, offset, seq_id0, B, gamma, u_accept, u_sample);
+  return (int)cudaGetLastError();
+}
+
+}  // extern "C"

@@ -1,0 +1,154 @@
+"""Drop-in n-gram storages (ngram_assisted/ngram_storage.py:5-249) backed by device hash tables
+(csrc/ngram.cu).  Same interface: next_token / has_gram / update / initialize / reset.
+
+Differences by design:
+  * tables live in HBM; `next_token` / `update` / `initialize` are one kernel launch for the batch;
+  * `table_ids` (optional) gives every sequence its own logical table -- the layout batched
+    n-gram-assisted decoding needs; default = one shared table, as in the reference;
+  * `lookup_chain` runs the gamma chained next_token() calls of ngram_assisted.py:95-99 in one launch;
+  * unknown contexts take a caller-supplied / Philox fallback token instead of torch.randint
+    (ngram_storage.py:84,165); an empty table is a miss, not a KeyError (:174).
+"""
+from __future__ import annotations
+
+import abc
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+class INgramStorage(abc.ABC):
+    """Interface of Ngram-Storage (ngram_assisted/ngram_storage.py:5-69)."""
+
+    def __init__(self, n: int, vocab_size: int):
+        assert n > 1, "n should be greater than 1"
+        self.n = n
+        self.vocab_size = vocab_size
+
+    @abc.abstractmethod
+    def next_token(self, input_ids: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]: ...
+
+    @abc.abstractmethod
+    def has_gram(self, ngram: torch.Tensor) -> bool: ...
+
+    @abc.abstractmethod
+    def update(self, input_ids: torch.Tensor, next_tokens: torch.Tensor): ...
+
+    @abc.abstractmethod
+    def initialize(self, input_ids: torch.Tensor): ...
+
+    @abc.abstractmethod
+    def reset(self): ...
+
+
+class _DeviceNGram(INgramStorage):
+    _one_level = 0
+
+    def __init__(self, n: int, vocab_size: int, n_tables: int = 1, grams_per_table: int = 1 << 16,
+                 counts_per_table: int = 1 << 18, device="cuda", seed: int = 0):
+        super().__init__(n, vocab_size)
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("device n-gram tables need a CUDA device (no CPU fallback)")
+        self.n_tables = n_tables
+        self._h = C.c_void_p()
+        self._seed = seed
+        self._calls = 0
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_create(C.byref(self._h), n, vocab_size, n_tables, grams_per_table,
+                                                 counts_per_table, self._one_level), "specdec_ngram_create")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) is not None and self._h.value:
+                L.lib().specdec_ngram_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # -- helpers
+    def _prep(self, input_ids, lens, table_ids):
+        ids = input_ids if input_ids.dim() == 2 else input_ids.reshape(1, -1)
+        ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
+        B, ml = ids.shape
+        if lens is None:
+            lens = torch.full((B,), ml, dtype=torch.int32, device=self.device)
+        else:
+            lens = lens.to(device=self.device, dtype=torch.int32).contiguous()
+        if table_ids is not None:
+            table_ids = table_ids.to(device=self.device, dtype=torch.int32).contiguous()
+        return ids, lens, table_ids, B, ml
+
+    @staticmethod
+    def _p(t):
+        return None if t is None else t.data_ptr()
+
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _fallback(self, B, gamma):
+        g = torch.Generator(device="cpu").manual_seed(self._seed + self._calls)
+        self._calls += 1
+        return torch.randint(self.vocab_size, (B, gamma), generator=g).to(self.device)
+
+    # -- INgramStorage
+    def lookup_chain(self, input_ids, gamma: int, lens=None, table_ids=None, fallback=None):
+        ids, lens, table_ids, B, ml = self._prep(input_ids, lens, table_ids)
+        if fallback is None:
+            fallback = self._fallback(B, gamma)
+        fallback = fallback.to(device=self.device, dtype=torch.int64).reshape(B, gamma).contiguous()
+        drafts = torch.empty((B, gamma), dtype=torch.int64, device=self.device)
+        known = torch.empty((B, gamma), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_lookup_chain(self._h, self._p(ids), self._p(lens), self._p(table_ids), B, ml,
+                                                       gamma, self._p(fallback), self._p(drafts), self._p(known),
+                                                       self._stream()), "specdec_ngram_lookup_chain")
+        return drafts, known.bool()
+
+    def next_token(self, input_ids, lens=None, table_ids=None, fallback=None):
+        d, k = self.lookup_chain(input_ids, 1, lens, table_ids, fallback)
+        return d[:, 0], k[:, 0]
+
+    def update(self, input_ids, next_tokens, lens=None, table_ids=None):
+        ids, lens, table_ids, B, ml = self._prep(input_ids, lens, table_ids)
+        nt = next_tokens.to(device=self.device, dtype=torch.int64).reshape(B, -1).contiguous()
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_update(self._h, self._p(ids), self._p(lens), self._p(table_ids), B, ml,
+                                                 self._p(nt), nt.shape[1], self._stream()), "specdec_ngram_update")
+
+    def initialize(self, input_ids, lens=None, table_ids=None):
+        ids, lens, table_ids, B, ml = self._prep(input_ids, lens, table_ids)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_initialize(self._h, self._p(ids), self._p(lens), self._p(table_ids), B, ml,
+                                                     self._stream()), "specdec_ngram_initialize")
+
+    def reset(self):
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_reset(self._h, self._stream()), "specdec_ngram_reset")
+
+    def has_gram(self, ngram: torch.Tensor) -> bool:
+        """True iff the last token of `ngram` has been seen after its preceding context
+        (ngram_storage.py:98-106 / :181-193).  Implemented by probing best tokens is not enough, so the
+        check replays the lookup on the context and compares: exact for the arg-max token only."""
+        if ngram.shape[0] < 2:
+            return False
+        tok, known = self.next_token(ngram[:-1].reshape(1, -1))
+        return bool(known[0]) and int(tok[0]) == int(ngram[-1])
+
+    def status(self):
+        out = (C.c_int32 * 2)()
+        L.check(L.lib().specdec_ngram_status(self._h, out), "specdec_ngram_status")
+        return {"overflow": bool(out[0]), "grams_used_max": int(out[1])}
+
+
+class NGramStorage(_DeviceNGram):
+    """Multi-level storage: context lengths j in [2, n-1], longest first (ngram_storage.py:154-249)."""
+    _one_level = 0
+
+
+class OneLevelNGramStorage(_DeviceNGram):
+    """Single context length n-1 (ngram_storage.py:73-150)."""
+    _one_level = 1

@@ -1,0 +1,259 @@
+"""torch.library custom ops over the C ABI (host side stays Python/PyTorch; PyTorch is only
+device memory + streams here).  Every op requires CUDA tensors and the built library; there is
+no eager / CPU implementation behind them."""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+from torch import Tensor
+
+from . import _lib as L
+
+_DT = {torch.float32: L.F32, torch.bfloat16: L.BF16, torch.float16: L.F16}
+
+
+def _dtype_code(t: Tensor) -> int:
+    if t.dtype not in _DT:
+        raise TypeError(f"specdec: unsupported logits dtype {t.dtype} (float32 / bfloat16 / float16)")
+    return _DT[t.dtype]
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("specdec ops run on CUDA tensors only (no CPU fallback)")
+
+
+def _ptr(t: Optional[Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _rows_view(logits: Tensor) -> Tuple[Tensor, int, int, int]:
+    """[..., V] -> uniform row stride view (rows, V, stride)."""
+    V = logits.shape[-1]
+    x = logits if logits.stride(-1) == 1 else logits.contiguous()
+    x = x.reshape(-1, V)
+    if x.stride(-1) != 1:
+        x = x.contiguous()
+    return x, x.shape[0], V, (x.stride(0) if x.shape[0] > 1 else V)
+
+
+@torch.library.custom_op("specdec::verify", mutates_args=())
+def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_tokens: Tensor,
+              u_accept: Optional[Tensor], u_sample: Optional[Tensor], seed: int, offset: int, seq_id0: int,
+              temperature: float, top_k: int, top_p: float, sample_mode: int, flags: int,
+              stop_tokens: Optional[Tensor]) -> List[Tensor]:
+    _need_cuda(target_logits, draft_logits, draft_tokens, u_accept, u_sample, stop_tokens)
+    if target_logits.dim() != 3:
+        raise ValueError("target_logits must be [B, gamma(+1), V]")
+    B, gT, V = target_logits.shape
+    gamma = gT if (flags & L.NO_BONUS) else gT - 1
+    dev = target_logits.device
+    if target_logits.stride(-1) != 1:
+        target_logits = target_logits.contiguous()
+    dt = _dtype_code(target_logits)
+    if draft_logits is not None:
+        if draft_logits.dtype != target_logits.dtype:
+            draft_logits = draft_logits.to(target_logits.dtype)
+        if draft_logits.shape != (B, gamma, V):
+            raise ValueError(f"draft_logits must be [B={B}, gamma={gamma}, V={V}], got {tuple(draft_logits.shape)}")
+        if draft_logits.stride(-1) != 1:
+            draft_logits = draft_logits.contiguous()
+    draft_tokens = draft_tokens.to(device=dev, dtype=torch.int64).reshape(B, gamma).contiguous()
+    if u_accept is not None:
+        u_accept = u_accept.to(device=dev, dtype=torch.float32).reshape(B, gamma).contiguous()
+    if u_sample is not None:
+        u_sample = u_sample.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
+    n_stop = 0
+    if stop_tokens is not None:
+        stop_tokens = stop_tokens.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        n_stop = stop_tokens.numel()
+    n_acc = torch.empty(B, dtype=torch.int32, device=dev)
+    nxt = torch.empty(B, dtype=torch.int64, device=dev)
+    mask = torch.empty((B, gamma), dtype=torch.uint8, device=dev)
+    p_tok = torch.empty((B, gamma), dtype=torch.float32, device=dev)
+    q_tok = torch.empty((B, gamma), dtype=torch.float32, device=dev)
+    fstop = torch.empty(B, dtype=torch.int32, device=dev)
+    nprob = torch.empty(B, dtype=torch.float32, device=dev)
+    packed = torch.empty((B, gamma + 2), dtype=torch.int32, device=dev)
+    lib = L.lib()
+    ws_bytes = lib.specdec_workspace_bytes(B * (2 * gamma + 1))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    sd = draft_logits.stride() if draft_logits is not None else (0, 0, 1)
+    with torch.cuda.device(dev):
+        rc = lib.specdec_verify(
+            _ptr(target_logits), _ptr(draft_logits), dt, _ptr(draft_tokens), _ptr(u_accept), _ptr(u_sample),
+            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, seq_id0, B, gamma, V,
+            target_logits.stride(0), target_logits.stride(1), sd[0], sd[1],
+            float(temperature), int(top_k), float(top_p), int(sample_mode), int(flags),
+            _ptr(stop_tokens), n_stop, _ptr(n_acc), _ptr(nxt), _ptr(mask), _ptr(p_tok), _ptr(q_tok), _ptr(fstop),
+            _ptr(nprob), _ptr(packed), _ptr(ws), ws_bytes, _stream())
+    L.check(rc, "specdec_verify")
+    return [n_acc, nxt, mask, p_tok, q_tok, fstop, nprob, packed]
+
+
+@verify_op.register_fake
+def _(target_logits, draft_logits, draft_tokens, u_accept, u_sample, seed, offset, seq_id0, temperature, top_k,
+      top_p, sample_mode, flags, stop_tokens):
+    B, gT, V = target_logits.shape
+    gamma = gT if (flags & L.NO_BONUS) else gT - 1
+    e = target_logits.new_empty
+    return [e(B, dtype=torch.int32), e(B, dtype=torch.int64), e((B, gamma), dtype=torch.uint8),
+            e((B, gamma), dtype=torch.float32), e((B, gamma), dtype=torch.float32), e(B, dtype=torch.int32),
+            e(B, dtype=torch.float32), e((B, gamma + 2), dtype=torch.int32)]
+
+
+@torch.library.custom_op("specdec::process_probs", mutates_args=())
+def process_probs_op(logits: Tensor, temperature: float, top_k: int, top_p: float) -> List[Tensor]:
+    """-> [probs fp32 [..., V], row_stats [rows, 8]]  (LogitsProcessor.__call__, utils/logits_processor.py:13-15)"""
+    _need_cuda(logits)
+    x, rows, V, stride = _rows_view(logits)
+    dev = logits.device
+    probs = torch.empty((rows, V), dtype=torch.float32, device=dev)
+    stats = torch.empty((rows, 8), dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws_bytes = lib.specdec_workspace_bytes(rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.specdec_process_probs(_ptr(x), _dtype_code(x), rows, V, stride, float(temperature), int(top_k),
+                                       float(top_p), _ptr(probs), _ptr(stats), _ptr(ws), ws_bytes, _stream())
+    L.check(rc, "specdec_process_probs")
+    return [probs.reshape(logits.shape), stats]
+
+
+@process_probs_op.register_fake
+def _(logits, temperature, top_k, top_p):
+    rows = logits.numel() // logits.shape[-1]
+    return [logits.new_empty(logits.shape, dtype=torch.float32), logits.new_empty((rows, 8), dtype=torch.float32)]
+
+
+@torch.library.custom_op("specdec::sample_rows", mutates_args=())
+def sample_rows_op(logits: Tensor, u: Optional[Tensor], seed: int, offset: int, seq_id0: int, lane_id: int,
+                   temperature: float, top_k: int, top_p: float, sample_mode: int) -> List[Tensor]:
+    """processor + sample() fused: -> [tok int64 [rows], ptok fp32 [rows]]"""
+    _need_cuda(logits, u)
+    x, rows, V, stride = _rows_view(logits)
+    dev = logits.device
+    if u is not None:
+        u = u.to(device=dev, dtype=torch.float32).reshape(rows).contiguous()
+    tok = torch.empty(rows, dtype=torch.int64, device=dev)
+    ptok = torch.empty(rows, dtype=torch.float32, device=dev)
+    lib = L.lib()
+    ws_bytes = lib.specdec_workspace_bytes(rows)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.specdec_sample_rows(_ptr(x), _dtype_code(x), rows, V, stride, float(temperature), int(top_k),
+                                     float(top_p), int(sample_mode), _ptr(u), seed & 0xFFFFFFFFFFFFFFFF,
+                                     offset & 0xFFFFFFFFFFFFFFFF, seq_id0, lane_id, _ptr(tok), _ptr(ptok), _ptr(ws),
+                                     ws_bytes, _stream())
+    L.check(rc, "specdec_sample_rows")
+    return [tok, ptok]
+
+
+@sample_rows_op.register_fake
+def _(logits, u, seed, offset, seq_id0, lane_id, temperature, top_k, top_p, sample_mode):
+    rows = logits.numel() // logits.shape[-1]
+    return [logits.new_empty(rows, dtype=torch.int64), logits.new_empty(rows, dtype=torch.float32)]
+
+
+@torch.library.custom_op("specdec::sample_probs", mutates_args=())
+def sample_probs_op(probs: Tensor, u: Optional[Tensor], sample_mode: int) -> Tensor:
+    _need_cuda(probs, u)
+    V = probs.shape[-1]
+    p = probs.to(torch.float32).reshape(-1, V).contiguous()
+    rows = p.shape[0]
+    if u is not None:
+        u = u.to(device=p.device, dtype=torch.float32).reshape(rows).contiguous()
+    tok = torch.empty(rows, dtype=torch.int64, device=p.device)
+    with torch.cuda.device(p.device):
+        rc = L.lib().specdec_sample_probs(_ptr(p), rows, V, int(sample_mode), _ptr(u), _ptr(tok), _stream())
+    L.check(rc, "specdec_sample_probs")
+    return tok
+
+
+@sample_probs_op.register_fake
+def _(probs, u, sample_mode):
+    return probs.new_empty(probs.numel() // probs.shape[-1], dtype=torch.int64)
+
+
+def philox_uniform_op(seed: int, offset: int, seq_id0: int, B: int, gamma: int, device: torch.device) -> List[Tensor]:
+    """The exact uniforms specdec::verify draws when u_accept / u_sample are None."""
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("specdec ops run on CUDA tensors only (no CPU fallback)")
+    ua = torch.empty((B, gamma), dtype=torch.float32, device=device)
+    us = torch.empty(B, dtype=torch.float32, device=device)
+    with torch.cuda.device(device):
+        rc = L.lib().specdec_philox_uniform(seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, seq_id0, B, gamma,
+                                            _ptr(ua), _ptr(us), _stream())
+    L.check(rc, "specdec_philox_uniform")
+    return [ua, us]
+
+
+@torch.library.custom_op("specdec::prune_kv", mutates_args={"tensors", "seq_lens"})
+def prune_kv_op(tensors: List[Tensor], seq_lens: Tensor, discard: Tensor, zero_fill: bool) -> None:
+    """Per-sequence KV rollback on static [B,H,S_max,D] cache tensors (utils/caching.py:27-55 generalised)."""
+    _need_cuda(seq_lens, discard, *tensors)
+    if not tensors:
+        return
+    B, H, S, D = tensors[0].shape
+    for t in tensors:
+        if t.shape != (B, H, S, D) or not t.is_contiguous() or t.dtype != tensors[0].dtype:
+            raise ValueError("prune_kv: all cache tensors must be contiguous [B,H,S_max,D] of one dtype")
+    if seq_lens.dtype != torch.int32 or not seq_lens.is_contiguous():
+        raise ValueError("prune_kv: seq_lens must be a contiguous int32 tensor (updated in place)")
+    dev = seq_lens.device
+    discard = discard.to(device=dev, dtype=torch.int32).contiguous()
+    ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=dev)
+    with torch.cuda.device(dev):
+        rc = L.lib().specdec_prune_kv(_ptr(ptrs), len(tensors), B, H, S, D, tensors[0].element_size(),
+                                      _ptr(seq_lens), _ptr(discard), 1 if zero_fill else 0, _stream())
+    L.check(rc, "specdec_prune_kv")
+
+
+# ---- convenient python wrappers -------------------------------------------------------------
+class VerifyResult:
+    __slots__ = ("n_accepted", "next_token", "accept_mask", "p_tok", "q_tok", "first_stop", "next_prob", "packed")
+
+    def __init__(self, outs):
+        (self.n_accepted, self.next_token, self.accept_mask, self.p_tok, self.q_tok, self.first_stop,
+         self.next_prob, self.packed) = outs
+
+
+def fused_verify(target_logits, draft_logits, draft_tokens, u_accept=None, u_sample=None, *, seed=0, offset=0,
+                 seq_id0=0, temperature=1.0, top_k=0, top_p=1.0, greedy=False, flags=0, stop_tokens=None) -> VerifyResult:
+    if stop_tokens is not None and not isinstance(stop_tokens, Tensor):
+        stop_tokens = torch.as_tensor(list(stop_tokens), dtype=torch.int64, device=target_logits.device)
+    if stop_tokens is not None and stop_tokens.numel() == 0:
+        stop_tokens = None
+    return VerifyResult(verify_op(target_logits, draft_logits, draft_tokens, u_accept, u_sample, int(seed), int(offset),
+                                  int(seq_id0), float(temperature), int(top_k), float(top_p),
+                                  L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
+
+
+def process_probs(logits, temperature=1.0, top_k=0, top_p=1.0):
+    return process_probs_op(logits, float(temperature), int(top_k), float(top_p))
+
+
+def sample_rows(logits, u=None, *, seed=0, offset=0, seq_id0=0, lane_id=0, temperature=1.0, top_k=0, top_p=1.0,
+                greedy=False):
+    return sample_rows_op(logits, u, int(seed), int(offset), int(seq_id0), int(lane_id), float(temperature),
+                          int(top_k), float(top_p), L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF)
+
+
+def sample_probs(probs, u=None, greedy=False):
+    return sample_probs_op(probs, u, L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF)
+
+
+def philox_uniform(seed, offset, seq_id0, B, gamma, device="cuda"):
+    return philox_uniform_op(int(seed), int(offset), int(seq_id0), int(B), int(gamma), torch.device(device))
+
+
+def prune_kv(tensors, seq_lens, discard, zero_fill=True):
+    prune_kv_op(list(tensors), seq_lens, discard, bool(zero_fill))
+    return seq_lens

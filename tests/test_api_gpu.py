@@ -1,0 +1,160 @@
+"""GPU tests of the remaining C-ABI entry points and of the drop-in Python API."""
+import numpy as np
+import pytest
+import torch
+
+from cases import MODES, make_case
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_process_probs_matches_oracle(oracle_mod, mode, dtype):
+    import specdec_b200 as sd
+    m = MODES[mode]
+    z = make_case(B=3, gamma=2, V=32000, dtype=dtype, seed=4)["target"]
+    ref, st = oracle_mod.process_probs(z, temperature=m["temperature"], top_k=m["top_k"], top_p=m["top_p"])
+    probs, stats = sd.process_probs(z.cuda(), m["temperature"], m["top_k"], m["top_p"])
+    assert np.array_equal(probs.cpu().numpy(), ref)  # same canonical arithmetic => identical bits
+    assert np.array_equal(stats[:, 0].cpu().numpy(), st["m"]) and np.array_equal(stats[:, 1].cpu().numpy(), st["S32"])
+    np.testing.assert_allclose(probs.sum(-1).cpu().numpy(), 1.0, rtol=1e-5)
+    # against torch's own softmax (the reference's arithmetic): 1e-5 relative on everything that matters
+    if m["top_k"] == 0 and m["top_p"] >= 1.0:
+        t = torch.softmax(z.cuda().float() / m["temperature"], -1)
+        big = t > 1e-12
+        rel = ((probs - t).abs() / t)[big].max().item()
+        assert rel < 2e-5
+
+
+def test_processor_classes_api(oracle_mod):
+    import specdec_b200 as sd
+    z = make_case(B=2, gamma=1, V=5000, dtype="bf16", seed=8)["target"].cuda()
+    for proc, kw in [(sd.GreedyProcessor(), dict(temperature=1.0)), (sd.MultinomialProcessor(0.7), dict(temperature=0.7)),
+                     (sd.TopKProcessor(0.7, 50), dict(temperature=0.7, top_k=50)),
+                     (sd.NucleusProcessor(1.0, 0.9), dict(temperature=1.0, top_p=0.9)),
+                     (sd.TopKNucleusProcessor(0.7, 50, 0.9), dict(temperature=0.7, top_k=50, top_p=0.9))]:
+        zc = z.clone()
+        p = proc(zc)
+        assert torch.equal(zc, z), "logits must stay read-only"
+        assert p.shape == z.shape and p.dtype == z.dtype
+        ref, _ = oracle_mod.process_probs(z, **kw)
+        assert torch.equal(p.cpu(), torch.from_numpy(ref).to(z.dtype))
+        s = proc.sample(p)
+        assert s.shape == (*z.shape[:-1], 1) and s.dtype == torch.int64
+        masked = proc._process(z)
+        assert bool(((masked <= -1e19) == (torch.from_numpy(ref).cuda() == 0)).all()) or not kw.get("top_k") and not kw.get("top_p")
+    g = sd.GreedyProcessor()
+    assert torch.equal(g.sample(g(z)).squeeze(-1).cpu(), torch.from_numpy(oracle_mod.sample_probs(g(z).float().cpu().numpy(), None, greedy=True)).reshape(2, 2))
+
+
+@pytest.mark.parametrize("mode", ["greedy", "multinomial", "topk50_p0.9"])
+def test_sample_rows_and_probs(oracle_mod, mode):
+    import specdec_b200 as sd
+    m = MODES[mode]
+    z = make_case(B=8, gamma=2, V=32000, dtype="bf16", seed=6)["target"].reshape(-1, 32000)
+    u = torch.rand(z.shape[0], generator=torch.Generator().manual_seed(1))
+    tok, ptok = sd.sample_rows(z.cuda(), u.cuda(), **m)
+    otok, optok = oracle_mod.sample_rows(z, u.numpy(), **m)
+    assert np.array_equal(tok.cpu().numpy(), otok) and np.array_equal(ptok.cpu().numpy(), optok)
+    probs, _ = oracle_mod.process_probs(z, temperature=m["temperature"], top_k=m["top_k"], top_p=m["top_p"])
+    t2 = sd.sample_probs(torch.from_numpy(probs).cuda(), u.cuda(), greedy=m["greedy"])
+    assert np.array_equal(t2.cpu().numpy(), oracle_mod.sample_probs(probs, u.numpy(), greedy=m["greedy"]))
+
+
+def test_residual_resample_chi_square(oracle_mod):
+    """Distribution test (north_star): tokens emitted after a rejection follow norm(max(0,p-q))."""
+    import specdec_b200 as sd
+    from scipy import stats
+    V, N = 64, 20000
+    gen = torch.Generator().manual_seed(3)
+    t = 1.5 * torch.randn(1, 2, V, generator=gen)
+    d = 1.5 * torch.randn(1, 1, V, generator=gen)
+    p = torch.softmax(t[0, 0], -1); q = torch.softmax(d[0, 0], -1)
+    tok = int(torch.argmax(q / p))  # a draft that is (almost) always rejected
+    r = sd.fused_verify(t.cuda().expand(N, 2, V), d.cuda().expand(N, 1, V), torch.full((N, 1), tok).cuda(), None, None,
+                        seed=99, offset=0)
+    rej = r.n_accepted.cpu() == 0
+    assert rej.float().mean() > 0.5
+    xs = r.next_token.cpu()[rej].numpy()
+    resid = torch.clamp(p - q, min=0); resid = (resid / resid.sum()).numpy()
+    obs = np.bincount(xs, minlength=V).astype(np.float64)
+    keep = resid * len(xs) >= 5
+    chi, pval = stats.chisquare(np.append(obs[keep], obs[~keep].sum()),
+                                np.append(resid[keep], resid[~keep].sum()) * len(xs))
+    assert pval > 1e-3, (chi, pval)
+    # acceptance frequency ~ min(1, p/q)
+    acc_rate = 1.0 - rej.float().mean().item()
+    assert abs(acc_rate - min(1.0, float(p[tok] / q[tok]))) < 0.02
+
+
+def test_prune_kv_matches_reference_view_semantics(oracle_mod):
+    import specdec_b200 as sd
+    B, H, S, D = 5, 3, 40, 16
+    gen = torch.Generator().manual_seed(0)
+    tensors = [torch.randn(B, H, S, D, generator=gen).to(torch.bfloat16) for _ in range(4)]
+    lens = torch.tensor([40, 17, 5, 1, 0], dtype=torch.int32)
+    disc = torch.tensor([3, 5, 5, 4, 2], dtype=torch.int32)
+    dev = [t.cuda() for t in tensors]
+    dl = lens.cuda()
+    sd.prune_kv(dev, dl, disc.cuda(), True)
+    exp = [t.clone().view(torch.int16).numpy() for t in tensors]
+    new = oracle_mod.prune_kv(exp, lens.numpy(), disc.numpy(), True)
+    assert np.array_equal(dl.cpu().numpy(), new)
+    for a, b in zip(dev, exp):
+        assert np.array_equal(a.cpu().view(torch.int16).numpy(), b)
+    # the valid prefix equals the reference's per-sequence view tensor[:, :, :-n, :]
+    for b in range(B):
+        n = int(min(disc[b], lens[b])); L0 = int(lens[b])
+        if L0 - n > 0:
+            ref_view = tensors[0][b:b + 1, :, :L0, :][:, :, :L0 - n, :] if n > 0 else tensors[0][b:b + 1, :, :L0, :]
+            assert torch.equal(dev[0][b:b + 1, :, :L0 - n, :].cpu(), ref_view)
+    # drop-in prune_cache on tuple caches is the same zero-copy view as the reference
+    cache = tuple((t[:1], t[:1]) for t in dev[:2])
+    pr = sd.prune_cache(cache, 4)
+    assert pr[0][0].shape[2] == S - 4 and pr[0][0].data_ptr() == cache[0][0].data_ptr()
+    with pytest.raises(ValueError):
+        sd.prune_cache([1, 2], 1)
+
+
+@pytest.mark.parametrize("one_level", [False, True])
+def test_ngram_tables_match_oracle(one_level):
+    import specdec_b200 as sd
+    from oracle.ngram_oracle import NGramOracle
+    rng = np.random.RandomState(0)
+    V, n, B = 50, 4, 6
+    cls = sd.OneLevelNGramStorage if one_level else sd.NGramStorage
+    # (a) shared table, as in the reference; (b) one table per sequence
+    for per_seq in (False, True):
+        st = cls(n, V, n_tables=B if per_seq else 1, grams_per_table=4096, counts_per_table=8192)
+        orc = NGramOracle(n, V, one_level)
+        tabs = torch.arange(B, dtype=torch.int32) if per_seq else None
+        seqs = rng.randint(0, 6, size=(B, 30))  # tiny alphabet => many repeated contexts
+        lens = rng.randint(0, 31, size=B).astype(np.int32); lens[0] = 30; lens[1] = 2
+        ids = torch.from_numpy(seqs)
+        st.initialize(ids, torch.from_numpy(lens), tabs)
+        orc.initialize([seqs[i, :lens[i]] for i in range(B)], None if tabs is None else tabs.tolist())
+        for step in range(12):
+            nt = rng.randint(0, 6, size=(B, 1 + step % 3))
+            st.update(ids, torch.from_numpy(nt), torch.from_numpy(lens), tabs)
+            orc.update([seqs[i, :lens[i]] for i in range(B)], nt, None if tabs is None else tabs.tolist())
+            fb = rng.randint(0, V, size=(B, 5))
+            d, k = st.lookup_chain(ids, 5, torch.from_numpy(lens), tabs, torch.from_numpy(fb))
+            od, ok = orc.lookup_chain([seqs[i, :lens[i]] for i in range(B)], 5, None if tabs is None else tabs.tolist(), fb)
+            assert d.cpu().tolist() == od and k.cpu().tolist() == ok
+            lens = np.maximum(lens - (step % 2), 0).astype(np.int32)
+        assert not st.status()["overflow"]
+        st.reset()
+        d, k = st.lookup_chain(ids, 2, torch.from_numpy(lens), tabs, torch.zeros(B, 2, dtype=torch.long))
+        assert not bool(k.any())
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    import specdec_b200 as sd
+    monkeypatch.setattr(sd._lib, "_lib", None)
+    monkeypatch.setattr(sd._lib, "LIB_PATH", "/nonexistent/libspecdec_b200.so")
+    with pytest.raises(RuntimeError, match="no CPU"):
+        sd.process_probs(torch.zeros(1, 8, device="cuda"))
+    with pytest.raises(RuntimeError, match="CUDA tensors only"):
+        sd.ops.verify_op(torch.zeros(1, 2, 8), torch.zeros(1, 1, 8), torch.zeros(1, 1, dtype=torch.long), None, None,
+                         0, 0, 0, 1.0, 0, 1.0, 1, 0, None)

@@ -1,0 +1,202 @@
+"""Parity of the CUDA verify path (through the C ABI / torch ops) with the CPU oracle: accepted
+lengths, emitted tokens, accept masks, stop indices BIT-EXACT; probabilities within 1e-5 (they are in
+fact bit-identical because both sides use the same canonical arithmetic)."""
+import numpy as np
+import pytest
+import torch
+
+from cases import MODES, make_case
+
+pytestmark = pytest.mark.gpu
+
+F_BATCHED, F_NO_BONUS, F_SKIP, F_NGRAM, F_FALLBACK = 1, 2, 4, 8, 16
+
+
+def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
+    import specdec_b200 as sd
+    m = MODES[mode]
+    ngram = bool(flags & F_NGRAM)
+    tgt = case["target"][:, :-1] if (flags & F_NO_BONUS) else case["target"]
+    o = oracle.verify(tgt if not (flags & F_NO_BONUS) else case["target"], None if ngram else case["draft"],
+                      case["draft_tokens"], case["u_accept"], case["u_sample"], flags=flags, stop_tokens=stop, **m)
+    r = sd.fused_verify(tgt.to(dev), None if ngram else case["draft"].to(dev), case["draft_tokens"].to(dev),
+                        case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
+    torch.cuda.synchronize()
+    return o, r
+
+
+def _assert_same(o, r, ngram=False):
+    assert np.array_equal(r.n_accepted.cpu().numpy(), o.n_accepted), "accepted lengths differ"
+    assert np.array_equal(r.next_token.cpu().numpy(), o.next_token), "emitted tokens differ"
+    assert np.array_equal(r.accept_mask.cpu().numpy(), o.accept_mask), "accept masks differ"
+    assert np.array_equal(r.first_stop.cpu().numpy(), o.first_stop), "stop index differs"
+    np.testing.assert_allclose(r.p_tok.cpu().numpy(), o.p_tok, rtol=1e-5, atol=0)
+    if not ngram:
+        np.testing.assert_allclose(r.q_tok.cpu().numpy(), o.q_tok, rtol=1e-5, atol=0)
+    # packed = {n, accepted drafts, next, -1...}
+    pk = r.packed.cpu().numpy()
+    assert np.array_equal(pk[:, 0], o.n_accepted)
+    for b in range(pk.shape[0]):
+        n = int(o.n_accepted[b])
+        assert pk[b, 1 + n] == o.next_token[b]
+
+
+@pytest.mark.parametrize("mode", list(MODES))
+@pytest.mark.parametrize("dtype", ["f32", "bf16", "f16"])
+@pytest.mark.parametrize("V", [1000, 32000])
+def test_verify_modes(oracle_mod, mode, dtype, V):
+    case = make_case(B=6, gamma=4, V=V, dtype=dtype, sigma=0.5, seed=V % 97, oracle=oracle_mod, mode=mode)
+    o, r = _run_both(oracle_mod, case, mode)
+    _assert_same(o, r)
+
+
+@pytest.mark.parametrize("mode", ["multinomial", "topk50", "nucleus0.9", "topk50_p0.9", "greedy"])
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+def test_verify_llama_vocab(oracle_mod, mode, dtype):
+    case = make_case(B=8, gamma=4, V=128256, dtype=dtype, sigma=0.5, seed=5, oracle=oracle_mod, mode=mode)
+    o, r = _run_both(oracle_mod, case, mode)
+    _assert_same(o, r)
+    assert 0 < o.n_accepted.sum() < 8 * 4  # the case exercises both accept and reject
+
+
+@pytest.mark.parametrize("V", [7, 257, 4099, 50257])  # ragged: odd V => rows not 16-byte aligned
+@pytest.mark.parametrize("dtype", ["f32", "bf16"])
+@pytest.mark.parametrize("mode", ["multinomial", "topk50_p0.9", "nucleus0.9"])
+def test_verify_ragged_vocab(oracle_mod, V, dtype, mode):
+    case = make_case(B=3, gamma=3, V=V, dtype=dtype, sigma=1.0, seed=V, oracle=oracle_mod, mode=mode)
+    o, r = _run_both(oracle_mod, case, mode)
+    _assert_same(o, r)
+
+
+@pytest.mark.parametrize("gamma", [1, 2, 5, 8])
+@pytest.mark.parametrize("sigma", [0.0, 3.0])
+def test_verify_gamma_and_acceptance_extremes(oracle_mod, gamma, sigma):
+    case = make_case(B=5, gamma=gamma, V=8192, dtype="bf16", sigma=sigma, seed=gamma, oracle=oracle_mod)
+    o, r = _run_both(oracle_mod, case, "multinomial")
+    _assert_same(o, r)
+    if sigma == 0.0:
+        assert (o.n_accepted == gamma).all()  # p == q: everything accepted, bonus row drawn
+
+
+@pytest.mark.parametrize("flags", [F_SKIP, F_BATCHED | F_NO_BONUS | F_FALLBACK, F_BATCHED, F_NO_BONUS])
+@pytest.mark.parametrize("mode", ["multinomial", "greedy", "topk50"])
+def test_verify_variant_flags(oracle_mod, flags, mode):
+    case = make_case(B=6, gamma=4, V=32000, dtype="f32", sigma=0.7, seed=11 + flags, oracle=oracle_mod, mode=mode)
+    o, r = _run_both(oracle_mod, case, mode, flags=flags)
+    _assert_same(o, r)
+
+
+@pytest.mark.parametrize("mode", ["greedy", "multinomial", "topk50"])
+def test_verify_ngram_mode(oracle_mod, mode):
+    case = make_case(B=6, gamma=4, V=32000, dtype="bf16", sigma=0.0, seed=3, kind="peaked")
+    m = MODES[mode]
+    # drafts = what the target itself would pick for the first positions, then garbage => partial accepts
+    tok, _ = oracle_mod.sample_rows(case["target"][:, :4].float().numpy().reshape(24, 32000),
+                                    case["u_accept"].numpy().reshape(-1), **m)
+    toks = torch.from_numpy(tok.reshape(6, 4)).clone()
+    toks[::2, 2] = 17
+    case["draft_tokens"] = toks
+    o, r = _run_both(oracle_mod, case, mode, flags=F_NGRAM)
+    _assert_same(o, r, ngram=True)
+    assert o.n_accepted.max() == 4 and o.n_accepted.min() == 2
+
+
+def test_verify_stop_tokens(oracle_mod):
+    case = make_case(B=8, gamma=4, V=4096, dtype="f32", sigma=0.0, seed=21, oracle=oracle_mod)
+    stop = [int(case["draft_tokens"][0, 1]), int(case["draft_tokens"][3, 0]), 4095]
+    o, r = _run_both(oracle_mod, case, "multinomial", stop=stop)
+    _assert_same(o, r)
+    assert o.first_stop[0] in (0, 1) and o.first_stop[3] == 0
+
+
+def test_verify_adversarial_rows(oracle_mod):
+    """all-equal logits (ties everywhere), one-hot rows, -inf entries, p == q."""
+    B, g, V = 4, 3, 2048
+    t = torch.zeros(B, g + 1, V)
+    d = torch.zeros(B, g, V)
+    t[1] = -30.0; t[1, :, 5] = 10.0          # one-hot-ish
+    d[1] = -30.0; d[1, :, 5] = 10.0
+    t[2] = torch.randn(g + 1, V); t[2, :, ::3] = float("-inf")
+    d[2] = torch.randn(g, V); d[2, :, ::3] = float("-inf")
+    t[3] = torch.randn(g + 1, V).round()     # many exact ties
+    d[3] = t[3, :g]
+    toks = torch.tensor([[0, 7, 2047], [5, 5, 5], [1, 2, 4], [9, 10, 11]])
+    case = dict(target=t, draft=d, draft_tokens=toks, u_accept=torch.tensor([[0.1, 0.5, 0.999]] * B),
+                u_sample=torch.tensor([0.0, 0.3, 0.77, 0.99999]))
+    for mode in ["multinomial", "greedy", "topk50", "nucleus0.9", "topk50_p0.9"]:
+        o, r = _run_both(oracle_mod, case, mode)
+        _assert_same(o, r)
+
+
+def test_strided_logits_views(oracle_mod):
+    """target_logits as a slice of a longer [B, L, V] model output (non-contiguous batch stride)."""
+    import specdec_b200 as sd
+    case = make_case(B=4, gamma=3, V=4096, dtype="bf16", sigma=0.5, seed=9, oracle=oracle_mod)
+    full = torch.zeros(4, 10, 4096, dtype=torch.bfloat16)
+    full[:, 5:9] = case["target"]
+    view = full.cuda()[:, 5:9]
+    m = MODES["multinomial"]
+    r = sd.fused_verify(view, case["draft"].cuda(), case["draft_tokens"].cuda(), case["u_accept"].cuda(),
+                        case["u_sample"].cuda(), **m)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
+    _assert_same(o, r)
+
+
+def test_philox_matches_oracle_and_is_sharding_independent(oracle_mod):
+    import specdec_b200 as sd
+    ua, us = sd.philox_uniform(2025, 7, 100, 16, 4)
+    oa, os_ = oracle_mod.philox_uniform(2025, 7, 100, 16, 4)
+    assert np.array_equal(ua.cpu().numpy(), oa) and np.array_equal(us.cpu().numpy(), os_)
+    ua2, us2 = sd.philox_uniform(2025, 7, 108, 8, 4)  # second half as its own shard
+    assert torch.equal(ua2, ua[8:]) and torch.equal(us2, us[8:])
+    assert 0.0 <= float(ua.min()) and float(ua.max()) < 1.0
+    # in-kernel uniforms == dumped uniforms
+    case = make_case(B=16, gamma=4, V=4096, dtype="f32", sigma=0.5, seed=2, oracle=oracle_mod)
+    r1 = sd.fused_verify(case["target"].cuda(), case["draft"].cuda(), case["draft_tokens"].cuda(), None, None,
+                         seed=2025, offset=7, seq_id0=100)
+    r2 = sd.fused_verify(case["target"].cuda(), case["draft"].cuda(), case["draft_tokens"].cuda(), ua, us)
+    assert torch.equal(r1.n_accepted, r2.n_accepted) and torch.equal(r1.next_token, r2.next_token)
+
+
+def test_full_size_properties():
+    """BASELINE.json full size (B=256, gamma=4, V=128256, bf16): size-independent properties.
+    p == q  =>  every draft accepted for any u; greedy bonus token == argmax of the bonus row;
+    shuffling the batch permutes the outputs (results do not depend on the row's CTA)."""
+    import specdec_b200 as sd
+    B, g, V = 256, 4, 128256
+    gen = torch.Generator(device="cuda").manual_seed(0)
+    t = (3 * torch.randn(B, g + 1, V, device="cuda", generator=gen)).to(torch.bfloat16)
+    toks = torch.randint(V, (B, g), device="cuda", generator=gen)
+    ua = torch.rand(B, g, device="cuda", generator=gen)
+    us = torch.rand(B, device="cuda", generator=gen)
+    r = sd.fused_verify(t, t[:, :g].contiguous(), toks, ua, us, greedy=True)
+    assert bool((r.n_accepted == g).all())
+    assert torch.equal(r.next_token, t[:, g].float().argmax(-1))
+    np.testing.assert_allclose(r.p_tok.cpu().numpy(), r.q_tok.cpu().numpy(), rtol=0, atol=0)
+    ref_p = torch.softmax(t[:, :g].float(), -1).gather(-1, toks.unsqueeze(-1)).squeeze(-1)
+    np.testing.assert_allclose(r.p_tok.cpu().numpy(), ref_p.cpu().numpy(), rtol=2e-5, atol=1e-30)
+    d = (t[:, :g].float() + 0.5 * torch.randn(B, g, V, device="cuda", generator=gen)).to(torch.bfloat16)
+    r1 = sd.fused_verify(t, d, toks, ua, us)
+    perm = torch.randperm(B, device="cuda", generator=gen)
+    r2 = sd.fused_verify(t[perm].contiguous(), d[perm].contiguous(), toks[perm], ua[perm], us[perm])
+    assert torch.equal(r1.n_accepted[perm], r2.n_accepted) and torch.equal(r1.next_token[perm], r2.next_token)
+    assert 0 < int(r1.n_accepted.sum()) < B * g
+
+
+@pytest.mark.parametrize("mode_kw", [dict(temperature=1.0, top_k=0, top_p=0.9, greedy=False),
+                                     dict(temperature=0.8, top_k=2000, top_p=1.0, greedy=False),
+                                     dict(temperature=0.8, top_k=3000, top_p=0.95, greedy=False)])
+def test_slow_selection_path(oracle_mod, mode_kw):
+    """flat / tied rows whose kept set exceeds the shared-memory candidate capacity (8192) or whose
+    top_k exceeds 1024 take the sweep-based exact selection."""
+    import specdec_b200 as sd
+    B, g, V = 2, 1, 20000
+    gen = torch.Generator().manual_seed(5)
+    t = 0.01 * torch.randn(B, g + 1, V, generator=gen)
+    t[1] = 0.0  # every logit tied: nucleus keeps the first ceil(0.9 V) indices
+    d = t[:, :g] + 0.01 * torch.randn(B, g, V, generator=gen)
+    toks = torch.tensor([[3], [19999]])
+    ua = torch.tensor([[0.5], [0.99]]); us = torch.tensor([0.25, 0.9])
+    o = oracle_mod.verify(t, d, toks, ua, us, **mode_kw)
+    r = sd.fused_verify(t.cuda(), d.cuda(), toks.cuda(), ua.cuda(), us.cuda(), **mode_kw)
+    _assert_same(o, r)
