@@ -54,9 +54,10 @@ typedef struct CUstream_st* specdec_stream_t; /* == cudaStream_t */
 SPECDEC_API int specdec_version(void);
 SPECDEC_API const char* specdec_error_string(int code);
 
-/* Workspace needed by specdec_verify / specdec_process_probs / specdec_sample_rows for `rows`
- * logit rows (verify: rows = B*(2*gamma+1)). */
-SPECDEC_API size_t specdec_workspace_bytes(int64_t rows);
+/* Workspace sizes (bytes) for the three row-processing entry points. */
+SPECDEC_API size_t specdec_workspace_bytes(int64_t rows);          /* specdec_process_probs */
+SPECDEC_API size_t specdec_verify_workspace_bytes(int B, int gamma, int V);
+SPECDEC_API size_t specdec_sample_rows_workspace_bytes(int64_t rows, int V);
 
 /*
  * One speculative verify step for B sequences: replaces, per sequence,

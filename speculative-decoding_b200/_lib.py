@@ -19,6 +19,8 @@ _SIGS = {
     "specdec_version": (C.c_int, []),
     "specdec_error_string": (C.c_char_p, [_i]),
     "specdec_workspace_bytes": (_sz, [_i64]),
+    "specdec_verify_workspace_bytes": (_sz, [_i, _i, _i]),
+    "specdec_sample_rows_workspace_bytes": (_sz, [_i64, _i]),
     "specdec_verify": (_i, [_vp, _vp, _i, _vp, _vp, _vp, _u64, _u64, _i64, _i, _i, _i, _i64, _i64, _i64, _i64,
                             _f, _i, _f, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "specdec_set_profile_events": (_i, [_vp, _vp, _vp]),

@@ -1,0 +1,472 @@
+// hybrid.cuh -- the production verify pipeline (included by verify.cu).
+//
+// The canonical (oracle-reproducible) arithmetic costs ~16 issue slots per logit because exp2 is a
+// polynomial on the FMA pipe.  Only a few rows per sequence actually need it, so the step is split:
+//
+//   rowfast_kernel   every row, ONE pass over HBM: online max + sum of MUFU ex2 (5 slots/logit).
+//                    The row max is exact; the sum is good to ~1e-6 relative.
+//   plan_kernel      per sequence: p~/q~ of the draft tokens from the fast sums and the accept test
+//                    with a 1e-3 relative safety margin => sure-accept / sure-reject / ambiguous.
+//                    Rows that decide something (ambiguous positions + the first sure reject, whose
+//                    residual needs exact normalisers) become tasks.
+//   exact_rows_kernel canonical sum of the task rows (u64 atomics: order independent).
+//   sample_partial_kernel  final decisions from exact sums where they exist (identical to the
+//                    oracle's because the fast ones are only trusted outside the margin), then the
+//                    one sweep the next token needs -- residual max(0,p-q) or the bonus/target row --
+//                    as per-256-element integer partial sums, CH CTAs per sequence.
+//   sample_final_kernel    scan of the partials, inverse-CDF location, token + packed result.
+//
+// top-k / nucleus modes use the exact rowstats_kernel for every row (their kept sets need exact
+// masses) and skip plan/exact tasks.  Outputs are bit-identical to the exact-everywhere path.
+#pragma once
+// (included inside namespace specdec)
+
+constexpr int FT = 512;   // threads, rowfast_kernel
+constexpr int PT = 256;   // threads, chunk kernels
+constexpr int CH = 8;     // CTAs per row (pair) in exact_rows / sample_partial
+constexpr int ST_ACCEPT = 0, ST_REJECT = 1, ST_AMBIG = 2, ST_EXACTROW = 3, ST_NEED = 4;
+constexpr float MARGIN = 1e-3f;
+
+struct HybridWs {
+  u64* acc;               // [R]  canonical Sfix of task rows
+  int* tasks;             // [B*gamma]
+  int* ntasks;            // [1]
+  unsigned char* status;  // [B*gamma]
+  u64* part;              // [B][nseg_pad]
+  u64* tot;               // [B]
+  u64* best;              // [B]  greedy: (value bits << 32) | ~index
+  int* samp;              // [B][4]: n, mode, p-row position, unused
+  int nseg_pad;
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(FT, 2) rowfast_kernel(RowJob job) {
+  __shared__ float shf[33];
+  const long long r = blockIdx.x;
+  const void* row = row_ptr<DT>(job, r);
+  const bool aligned = (((size_t)row) & 15) == 0;
+  const int V = job.V, NV = (V + 7) >> 3;
+  const float c = job.c;
+  float m = -INFINITY, s = 0.0f;
+  sweep_range<DT, FT>(row, V, aligned, 0, NV, [&](const float(&x)[8], int) {
+    float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    if (vm > m) {  // rare after the first few vectors
+      s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c)));
+      m = vm;
+    }
+    const float mc = __fmul_rn(m, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
+  });
+  const float M = block_max_f(m, shf);
+  s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, M), c))) : 0.0f;
+  // block sum (fp32 tree; this sum is only trusted to ~1e-6)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) shf[w] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (lane < FT / 32) ? shf[lane] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      RowOut o;
+      o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, t);
+      o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
+      job.out[r] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float job_u_accept(const DecideJob& job, int b, int i) {
+  return job.u_accept ? job.u_accept[(long long)b * job.gamma + i]
+                      : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)i);
+}
+__device__ __forceinline__ int accept_rule(float p, float q, float u, int flags) {
+  if (flags & SPECDEC_ACCEPT_BATCHED) {  // engine/infer_engine.py:303-305 (python floats = double)
+    const double ap = (q <= 0.0f) ? 1.0 : fmin(1.0, (double)p / (double)q);
+    return ((double)u < ap) ? 1 : 0;
+  }
+  const float frac = __fdiv_rn(p, q);  // sampling/speculative_decoding.py:143 (NaN => accept)
+  return !(u > frac) ? 1 : 0;
+}
+
+// one warp per sequence, one lane per draft position
+template <int DT>
+__global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const RowJob& rj = job.rj;
+  const int g = job.gamma, rps = rj.nT + rj.nD;
+  if (b >= (int)(rj.R / rps)) return;
+  const RowOut* ro = rj.out + (long long)b * rps;
+  const long long* toks = job.draft_tokens + (long long)b * g;
+  bool have_reject = false;
+  for (int i0 = 0; i0 < g; i0 += 32) {
+    const int i = i0 + lane;
+    int st = ST_ACCEPT;
+    bool exact_row = false;
+    if (i < g) {
+      const RowOut rp = ro[i];
+      const RowOut rq = ro[rj.nT + i];
+      if (rp.flags & 1) {
+        st = ST_EXACTROW; exact_row = true;
+      } else {
+        const int tok = (int)min(max(toks[i], 0ll), (long long)rj.V - 1);
+        const float zp = load1<DT>(row_ptr<DT>(rj, (long long)b * rps + i), tok);
+        const float zq = load1<DT>(row_ptr<DT>(rj, (long long)b * rps + rj.nT + i), tok);
+        const float p = exp2f(__fmaf_rn(zp, rj.c, -rp.mc)) * rp.inv;
+        const float q = exp2f(__fmaf_rn(zq, rj.c, -rq.mc)) * rq.inv;
+        job.p_tok[(long long)b * g + i] = p;
+        job.q_tok[(long long)b * g + i] = q;
+        const float u = job_u_accept(job, b, i);
+        st = ST_AMBIG;
+        if (p > 1e-30f && q > 1e-30f && p < 1e30f && q < 1e30f) {
+          const float r = p / q, lo = r * (1.0f - MARGIN), hi = r * (1.0f + MARGIN);
+          if (job.flags & SPECDEC_ACCEPT_BATCHED) {
+            if (u < fminf(1.0f, lo)) st = ST_ACCEPT;
+            else if (hi < 1.0f && u > hi) st = ST_REJECT;
+          } else {
+            if (u < lo) st = ST_ACCEPT;
+            else if (u > hi) st = ST_REJECT;
+          }
+        }
+      }
+    }
+    const unsigned rej = __ballot_sync(0xffffffffu, i < g && !exact_row && st == ST_REJECT);
+    bool need = (i < g) && !exact_row && (st == ST_AMBIG);
+    if (!have_reject && rej) {
+      if (lane == __ffs(rej) - 1) need = true;
+      have_reject = true;
+    }
+    if (i < g) {
+      if (need) {
+        st |= ST_NEED;
+        const int t = atomicAdd(ws.ntasks, 1);
+        ws.tasks[t] = b * g + i;
+      }
+      ws.status[(long long)b * g + i] = (unsigned char)st;
+    }
+  }
+}
+
+// canonical sums of the task rows: grid (B*gamma, CH)
+template <int DT>
+__global__ void __launch_bounds__(PT) exact_rows_kernel(DecideJob job, HybridWs ws) {
+  __shared__ u64 sh64[33];
+  if ((int)blockIdx.x >= *ws.ntasks) return;
+  const RowJob& rj = job.rj;
+  const int task = ws.tasks[blockIdx.x];
+  const int g = job.gamma, rps = rj.nT + rj.nD, V = rj.V;
+  const int b = task / g, i = task - b * g;
+  const int NV = (V + 7) >> 3, per = (NV + CH - 1) / CH;
+  const int v0 = blockIdx.y * per, v1 = min(NV, v0 + per);
+  const float c = rj.c;
+#pragma unroll 1
+  for (int which = 0; which < 2; ++which) {
+    const long long r = (long long)b * rps + (which ? rj.nT + i : i);
+    const void* row = row_ptr<DT>(rj, r);
+    const bool aligned = (((size_t)row) & 15) == 0;
+    const float mc = rj.out[r].mc;
+    u64 s = 0;
+    sweep_range<DT, PT>(row, V, aligned, v0, v1, [&](const float(&x)[8], int) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += fix40(cweight(x[k], c, mc));
+    });
+    s = block_sum_u64(s, sh64);
+    if (threadIdx.x == 0 && s) atomicAdd(&ws.acc[r], s);
+  }
+}
+
+// exact statistics of row r: from rowstats_kernel (masked modes) or from the exact task sums
+__device__ __forceinline__ RowOut resolved_row(const RowJob& rj, const HybridWs& ws, long long r) {
+  RowOut o = rj.out[r];
+  if (!(o.flags & 1)) {
+    const u64 S = ws.acc[r];
+    o.Sfix = S;
+    o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(S), 0x1p-40f));
+  }
+  return o;
+}
+
+struct SampleCtx {
+  const void* prow;
+  const void* qrow;
+  RowOut rp, rq;
+  bool pal, qal;
+  int V;
+  float c;
+  int resid;
+};
+// integer weights of vector v (8 elements); r_out (nullable) receives the fp32 residuals / weights
+template <int DT>
+__device__ __forceinline__ void sample_weights(const SampleCtx& sc, int v, u64 (&w)[8], float* vals) {
+  float xp[8];
+  load8<DT>(sc.prow, v, sc.V, sc.pal, xp);
+  if (sc.resid) {
+    float xq[8];
+    load8<DT>(sc.qrow, v, sc.V, sc.qal, xq);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = v * 8 + k;
+      float r = 0.0f;
+      if (j < sc.V) {
+        const float P = __fmul_rn(kept(sc.rp, xp[k], j) ? cweight(xp[k], sc.c, sc.rp.mc) : 0.0f, sc.rp.inv);
+        const float Q = __fmul_rn(kept(sc.rq, xq[k], j) ? cweight(xq[k], sc.c, sc.rq.mc) : 0.0f, sc.rq.inv);
+        r = __fsub_rn(P, Q);
+        r = r > 0.0f ? r : 0.0f;
+      }
+      w[k] = fix60(r);
+      if (vals) vals[k] = r;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = v * 8 + k;
+      const float e = (j < sc.V && kept(sc.rp, xp[k], j)) ? cweight(xp[k], sc.c, sc.rp.mc) : 0.0f;
+      w[k] = fix40(e);
+      if (vals) vals[k] = e;
+    }
+  }
+}
+
+// final accept decisions of sequence b, executed by one full warp (lane = position).
+// Returns n (all lanes); fills acc[] / pv[] / qv[] (pv < 0: keep the fast value already written).
+template <int DT>
+__device__ int final_decisions(const DecideJob& job, const HybridWs& ws, int b, int* acc, float* pv, float* qv) {
+  const RowJob& rj = job.rj;
+  const int g = job.gamma, rps = rj.nT + rj.nD, lane = threadIdx.x & 31;
+  const long long* toks = job.draft_tokens + (long long)b * g;
+  int n = g;
+  for (int i0 = 0; i0 < g; i0 += 32) {
+    const int i = i0 + lane;
+    int a = 1;
+    if (i < g) {
+      const int st = ws.status[(long long)b * g + i];
+      if ((st & ST_NEED) || (st & 3) == ST_EXACTROW) {
+        const int tok = (int)min(max(toks[i], 0ll), (long long)rj.V - 1);
+        const long long r1 = (long long)b * rps + i, r2 = (long long)b * rps + rj.nT + i;
+        const RowOut rp = resolved_row(rj, ws, r1), rq = resolved_row(rj, ws, r2);
+        const float p = row_prob<DT>(rp, row_ptr<DT>(rj, r1), tok, rj.c);
+        const float q = row_prob<DT>(rq, row_ptr<DT>(rj, r2), tok, rj.c);
+        a = accept_rule(p, q, job_u_accept(job, b, i), job.flags);
+        pv[i] = p; qv[i] = q;
+      } else {
+        a = ((st & 3) == ST_ACCEPT);
+        pv[i] = -1.0f;
+      }
+      acc[i] = a;
+    }
+    const unsigned rej = __ballot_sync(0xffffffffu, i < g && !a);
+    if (n == g && rej) n = i0 + __ffs(rej) - 1;
+  }
+  return n;
+}
+
+// grid (B, CH)
+template <int DT, bool MASKED, bool GREEDY>
+__global__ void __launch_bounds__(PT) sample_partial_kernel(DecideJob job, HybridWs ws) {
+  __shared__ u64 sh64[33];
+  __shared__ int s_acc[64];
+  __shared__ float s_p[64], s_q[64];
+  __shared__ int s_n, s_mode, s_prow;
+  const RowJob& rj = job.rj;
+  const int b = blockIdx.x, ch = blockIdx.y, g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (w == 0) {
+    const int n = final_decisions<DT>(job, ws, b, s_acc, s_p, s_q);
+    __syncwarp();
+    int mode = 0, prow = 0;  // 0 none, 1 target row, 2 residual
+    if (n == g) {
+      if (!(job.flags & SPECDEC_NO_BONUS)) { mode = 1; prow = g; }
+    } else if (job.flags & SPECDEC_SKIP_ADJUST) { mode = 1; prow = n; }
+    else { mode = 2; prow = n; }
+    if (lane == 0) { s_n = n; s_mode = mode; s_prow = prow; }
+    if (ch == 0) {
+      const long long* toks = job.draft_tokens + (long long)b * g;
+      for (int i = lane; i < g; i += 32) {
+        job.mask[(long long)b * g + i] = (unsigned char)s_acc[i];
+        if (s_p[i] >= 0.0f) { job.p_tok[(long long)b * g + i] = s_p[i]; job.q_tok[(long long)b * g + i] = s_q[i]; }
+      }
+      if (lane == 0) {
+        int fs = -1;
+        for (int i = 0; i < n && fs < 0; ++i)
+          for (int k = 0; k < job.n_stop; ++k)
+            if (toks[i] == job.stop[k]) { fs = i; break; }
+        job.n_acc[b] = n;
+        job.first_stop[b] = fs;
+        ws.samp[b * 4 + 0] = n; ws.samp[b * 4 + 1] = mode; ws.samp[b * 4 + 2] = prow;
+      }
+    }
+  }
+  __syncthreads();
+  const int mode = s_mode, prow = s_prow;
+  if (mode == 0) return;
+  const long long r1 = (long long)b * rps + prow;
+  const void* prowp = row_ptr<DT>(rj, r1);
+  const RowOut rp = resolved_row(rj, ws, r1);
+  const bool pal = (((size_t)prowp) & 15) == 0;
+  const void* qrowp = prowp;
+  RowOut rq = rp;
+  bool qal = pal;
+  if (mode == 2) {
+    const long long r2 = (long long)b * rps + rj.nT + prow;
+    qrowp = row_ptr<DT>(rj, r2);
+    rq = resolved_row(rj, ws, r2);
+    qal = (((size_t)qrowp) & 15) == 0;
+  }
+  const float c = rj.c;
+  const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
+  const int per = (nseg + CH - 1) / CH;
+  const int s0 = ch * per, s1 = min(nseg, s0 + per);
+  u64 tot = 0;
+  float best = (mode == 2) ? 0.0f : -1.0f;
+  int bidx = 0x7FFFFFFF;
+  u64* part = ws.part + (size_t)b * ws.nseg_pad;
+  // weights of one vector; both modes share the code shape so that two segments can be in flight
+  auto seg_sum = [&](const float(&xp)[8], const float(&xq)[8], int v) -> u64 {
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = v * 8 + k;
+      float val;
+      u64 wk;
+      if (mode == 2) {
+        const bool kp = !MASKED || kept(rp, xp[k], j), kq = !MASKED || kept(rq, xq[k], j);
+        const float P = __fmul_rn(kp ? cweight(xp[k], c, rp.mc) : 0.0f, rp.inv);
+        const float Q = __fmul_rn(kq ? cweight(xq[k], c, rq.mc) : 0.0f, rq.inv);
+        val = __fsub_rn(P, Q);
+        val = (val > 0.0f && j < V) ? val : 0.0f;
+        wk = fix60(val);
+      } else {
+        const bool kp = !MASKED || kept(rp, xp[k], j);
+        val = (kp && j < V) ? cweight(xp[k], c, rp.mc) : 0.0f;
+        wk = fix40(val);
+      }
+      s += wk;
+      if (GREEDY && j < V && val > best) { best = val; bidx = j; }
+    }
+    return s;
+  };
+  constexpr int WPB = PT / 32;
+  int seg = s0 + w;
+  for (; seg + WPB < s1; seg += 2 * WPB) {
+    const int va = seg * 32 + lane, vb = (seg + WPB) * 32 + lane;
+    float xpa[8], xqa[8], xpb[8], xqb[8];
+    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
+    load8<DT>(prowp, min(vb, NV - 1), V, pal, xpb);
+    if (mode == 2) {
+      load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
+      load8<DT>(qrowp, min(vb, NV - 1), V, qal, xqb);
+    }
+    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
+    u64 sb = (vb < NV) ? seg_sum(xpb, xqb, vb) : 0ull;
+    sa = warp_sum_u64(sa);
+    sb = warp_sum_u64(sb);
+    if (lane == 0) { part[seg] = sa; part[seg + WPB] = sb; tot += sa + sb; }
+  }
+  for (; seg < s1; seg += WPB) {
+    const int va = seg * 32 + lane;
+    float xpa[8], xqa[8];
+    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
+    if (mode == 2) load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
+    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
+    sa = warp_sum_u64(sa);
+    if (lane == 0) { part[seg] = sa; tot += sa; }
+  }
+  tot = block_sum_u64(tot, sh64);
+  if (threadIdx.x == 0 && tot) atomicAdd(&ws.tot[b], tot);
+  if (GREEDY) {
+    // (value, smallest index) max: non-negative floats order like their bit patterns
+    u64 key = (bidx == 0x7FFFFFFF) ? 0ull : (((u64)__float_as_uint(best)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bidx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
+    if (lane == 0 && key) atomicMax(&ws.best[b], key);
+  }
+}
+
+// grid B, NT threads
+template <int DT>
+__global__ void __launch_bounds__(NT, 1) sample_final_kernel(DecideJob job, HybridWs ws) {
+  __shared__ u64 part_sh[MAXPART];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ int shi[33];
+  __shared__ long long s_res;
+  const Scratch scr{part_sh, sh64, shf, shi, &s_res};
+  const RowJob& rj = job.rj;
+  const int b = blockIdx.x, g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
+  const int n = ws.samp[b * 4 + 0], mode = ws.samp[b * 4 + 1], prow = ws.samp[b * 4 + 2];
+  const bool greedy = job.greedy != 0;
+  const float us = job.u_sample ? job.u_sample[b]
+                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
+  long long x = -1;
+  bool from_p = false;
+  RowOut rp;
+  const void* prow_ptr = nullptr;
+  if (mode != 0) {
+    const long long r1 = (long long)b * rps + prow;
+    prow_ptr = row_ptr<DT>(rj, r1);
+    rp = resolved_row(rj, ws, r1);
+    const u64 total = ws.tot[b];
+    const u64 rmin = (job.flags & SPECDEC_RESID_FALLBACK) ? 1152921ull : 0ull;
+    if (mode == 2 && total <= rmin) {
+      // residual mass (numerically) zero: sample the target row itself (engine/infer_engine.py:319-321)
+      if (!(rp.flags & 1) && rp.Sfix == 0) {  // cannot happen: row n of a residual always has exact sums
+        rp.Sfix = 1; rp.inv = 1.0f;
+      }
+      x = sample_p_row<DT>(prow_ptr, rp, V, rj.c, greedy, us, scr);
+      from_p = true;
+    } else if (greedy) {
+      const u64 key = ws.best[b];
+      x = key ? (long long)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0ll;
+      from_p = (mode == 1);
+    } else {
+      SampleCtx sc;
+      sc.prow = prow_ptr; sc.rp = rp; sc.pal = (((size_t)prow_ptr) & 15) == 0;
+      sc.V = V; sc.c = rj.c; sc.resid = (mode == 2);
+      sc.qrow = prow_ptr; sc.rq = rp; sc.qal = sc.pal;
+      if (mode == 2) {
+        const long long r2 = (long long)b * rps + rj.nT + prow;
+        sc.qrow = row_ptr<DT>(rj, r2);
+        sc.rq = resolved_row(rj, ws, r2);
+        sc.qal = (((size_t)sc.qrow) & 15) == 0;
+      }
+      const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
+      auto wf = [&](int v, u64(&w)[8]) { sample_weights<DT>(sc, v, w, nullptr); };
+      x = locate_token(NV, nseg, ws.part + (size_t)b * ws.nseg_pad, total, scale_u24(total, u24_of(us)), wf, &s_res);
+      from_p = (mode == 1);
+    }
+  }
+  if (threadIdx.x == 0) {
+    job.next_tok[b] = x;
+    if (job.next_prob) {
+      float np = 0.0f;
+      if (from_p && x >= 0) {
+        if (mode == 1 && !(rp.flags & 1)) {  // target row sampled without a prior exact sum: total IS its Sfix
+          rp.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(ws.tot[b]), 0x1p-40f));
+        }
+        np = row_prob<DT>(rp, prow_ptr, (int)x, rj.c);
+      }
+      job.next_prob[b] = np;
+    }
+    if (job.packed) {
+      const long long* toks = job.draft_tokens + (long long)b * g;
+      int* pk = job.packed + (long long)b * (g + 2);
+      pk[0] = n;
+      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
+      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
+      pk[1 + n] = (int)x;
+    }
+  }
+}
+

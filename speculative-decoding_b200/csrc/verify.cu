@@ -52,6 +52,26 @@ __device__ __forceinline__ const void* row_ptr(const RowJob& job, long long r) {
 }
 
 // Visit every 8-element vector of a row: f(x[8], j0).  4 independent vector loads in flight.
+template <int DT, int NTH, typename F>
+__device__ __forceinline__ void sweep_range(const void* row, int V, bool aligned, int v_begin, int v_end, F f) {
+  int v = v_begin + threadIdx.x;
+  for (; v + 3 * NTH < v_end; v += 4 * NTH) {
+    float x0[8], x1[8], x2[8], x3[8];
+    load8<DT>(row, v, V, aligned, x0);
+    load8<DT>(row, v + NTH, V, aligned, x1);
+    load8<DT>(row, v + 2 * NTH, V, aligned, x2);
+    load8<DT>(row, v + 3 * NTH, V, aligned, x3);
+    f(x0, v * 8);
+    f(x1, (v + NTH) * 8);
+    f(x2, (v + 2 * NTH) * 8);
+    f(x3, (v + 3 * NTH) * 8);
+  }
+  for (; v < v_end; v += NTH) {
+    float x[8];
+    load8<DT>(row, v, V, aligned, x);
+    f(x, v * 8);
+  }
+}
 template <int DT, typename F>
 __device__ __forceinline__ void sweep(const void* row, int V, bool aligned, F f) {
   const int NV = (V + 7) >> 3;
@@ -313,7 +333,7 @@ __global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
       o.m = m; o.mc = mc;
       const float S32 = __fmul_rn(__ull2float_rn(Sfix), 0x1p-40f);
       o.inv = __fdiv_rn(1.0f, S32);
-      o.cut = cut; o.jcut = jcut; o.flags = 0; o.Sfix = Sfix;
+      o.cut = cut; o.jcut = jcut; o.flags = 1; o.Sfix = Sfix;
       job.out[r] = o;
     }
   }
@@ -332,63 +352,40 @@ __device__ __forceinline__ float row_prob(const RowOut& ro, const void* row, int
   return __fmul_rn(e, ro.inv);
 }
 
-// Inverse CDF over integer weights wf(v, w[8]) in index order: returns the first index whose
-// inclusive prefix sum exceeds target.  part[] receives the per-256-element partial sums.
-// total_out = sum of all weights.  If target >= total the result is -1.
+// Given the per-256-element partial sums of integer weights, find the first index whose inclusive
+// prefix sum exceeds target (warp 0 scans the partials, then re-evaluates one segment).  Block-wide
+// call; returns -1 if target >= total.
 template <typename WF>
-__device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in, unsigned u24, u64* part, u64* sh64,
-                                  long long* s_res, u64& total_out) {
-  const int NV = (V + 7) >> 3;
-  const int P = (NV + 31) >> 5;
+__device__ long long locate_token(int NV, int P, const u64* part, u64 total, u64 target, WF wf, long long* s_res) {
   const int lane = threadIdx.x & 31;
-  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += NT) {  // warp-uniform
-    const int v = base + lane;
-    u64 s = 0;
-    if (v < NV) {
-      u64 w[8];
-      wf(v, w);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) s += w[k];
-    }
-    s = warp_sum_u64(s);
-    if (lane == 0) part[base >> 5] = s;
-  }
-  __syncthreads();
-  u64 loc = 0;
-  for (int i = threadIdx.x; i < P; i += NT) loc += part[i];
-  const u64 total = block_sum_u64(loc, sh64);
-  total_out = total;
-  const u64 target = have_target ? target_in : scale_u24(total, u24);
   if (threadIdx.x < 32) {
     long long res = -1;
     if (target < total) {
-      // lane owns a contiguous chunk of partials
-      const int per = (P + 31) >> 5;
-      const int i0 = lane * per, i1 = min(P, i0 + per);
-      u64 cs = 0;
-      for (int i = i0; i < i1; ++i) cs += part[i];
-      u64 incl = cs;
+      // coalesced scan: 32 partials per step, all loads of a step independent
+      int seg = -1;
+      u64 before = 0, run = 0;
+      for (int base = 0; base < P && seg < 0; base += 128) {
+        u64 pv[4];
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-      }
-      const unsigned bal = __ballot_sync(0xffffffffu, incl > target);
-      const int owner = __ffs(bal) - 1;
-      int seg = 0;
-      u64 before = 0;
-      if (lane == owner) {
-        u64 run = incl - cs;
-        int i = i0;
-        for (; i < i1; ++i) {
-          if (run + part[i] > target) break;
-          run += part[i];
+        for (int q = 0; q < 4; ++q) { const int i = base + q * 32 + lane; pv[q] = (i < P) ? part[i] : 0ull; }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          u64 incl = pv[q];
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+          }
+          const unsigned bal = __ballot_sync(0xffffffffu, run + incl > target);
+          if (seg < 0 && bal) {
+            const int owner = __ffs(bal) - 1;
+            seg = base + q * 32 + owner;
+            before = run + __shfl_sync(0xffffffffu, incl - pv[q], owner);
+          }
+          run += __shfl_sync(0xffffffffu, incl, 31);
         }
-        seg = i; before = run;
       }
-      seg = __shfl_sync(0xffffffffu, seg, owner);
-      before = __shfl_sync(0xffffffffu, before, owner);
-      // evaluate the 256 elements of that segment
+      if (seg < 0) seg = 0;
       const int v = seg * 32 + lane;
       u64 w[8];
 #pragma unroll
@@ -424,6 +421,36 @@ __device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in,
   const long long out = *s_res;
   __syncthreads();
   return out;
+}
+
+// Inverse CDF over integer weights wf(v, w[8]) in index order: returns the first index whose
+// inclusive prefix sum exceeds target.  part[] receives the per-256-element partial sums.
+// total_out = sum of all weights.  If target >= total the result is -1.
+template <typename WF>
+__device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in, unsigned u24, u64* part, u64* sh64,
+                                  long long* s_res, u64& total_out) {
+  const int NV = (V + 7) >> 3;
+  const int P = (NV + 31) >> 5;
+  const int lane = threadIdx.x & 31;
+  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += NT) {  // warp-uniform
+    const int v = base + lane;
+    u64 s = 0;
+    if (v < NV) {
+      u64 w[8];
+      wf(v, w);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += w[k];
+    }
+    s = warp_sum_u64(s);
+    if (lane == 0) part[base >> 5] = s;
+  }
+  __syncthreads();
+  u64 loc = 0;
+  for (int i = threadIdx.x; i < P; i += NT) loc += part[i];
+  const u64 total = block_sum_u64(loc, sh64);
+  total_out = total;
+  const u64 target = have_target ? target_in : scale_u24(total, u24);
+  return locate_token(NV, P, part, total, target, wf, s_res);
 }
 
 // block-wide argmax, first index on ties; value must be >= 0; returns -1 if no value > floor_excl
@@ -663,6 +690,8 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
   }
 }
 
+#include "hybrid.cuh"
+
 // ---------------------------------------------------------------------------------------------
 // probabilities materialised (LogitsProcessor.__call__), sample() on given probs, philox dump
 // ---------------------------------------------------------------------------------------------
@@ -779,6 +808,77 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   return cudaGetLastError();
 }
 
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+struct WsLayout {
+  size_t rowout, zero, zero_bytes, tasks, status, samp, part, total;
+  int nseg_pad;
+};
+static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
+  WsLayout w;
+  const int NV = (V + 7) >> 3;
+  w.nseg_pad = ((NV + 31) >> 5) + 1;
+  size_t o = 0;
+  w.rowout = o; o = al256(o + (size_t)R * sizeof(RowOut));
+  w.zero = o;
+  o += (size_t)R * 8 + (size_t)B * 8 * 2 + 8;
+  w.zero_bytes = o - w.zero;
+  o = al256(o);
+  w.tasks = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1) * 4);
+  w.status = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1));
+  w.samp = o; o = al256(o + (size_t)B * 16);
+  w.part = o; o = al256(o + (size_t)B * w.nseg_pad * 8);
+  w.total = o;
+  return w;
+}
+static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, long long R) {
+  char* base = (char*)workspace;
+  HybridWs h;
+  h.acc = (u64*)(base + w.zero);
+  h.tot = h.acc + R;
+  h.best = h.tot + B;
+  h.ntasks = (int*)(h.best + B);
+  h.tasks = (int*)(base + w.tasks);
+  h.status = (unsigned char*)(base + w.status);
+  h.samp = (int*)(base + w.samp);
+  h.part = (u64*)(base + w.part);
+  h.nseg_pad = w.nseg_pad;
+  return h;
+}
+
+template <int DT>
+static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* workspace, int B, cudaStream_t st) {
+  const RowJob& rj = dj.rj;
+  const bool masked = rj.top_k > 0 || rj.use_p;
+  HybridWs ws = ws_pointers(wl, workspace, B, rj.R);
+  cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st);
+  if (e != cudaSuccess) return e;
+  if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+  if (masked) {
+    e = launch_rowstats<DT>(rj, st);
+    if (e != cudaSuccess) return e;
+  } else {
+    rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(rj);
+  }
+  if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+  if (dj.gamma > 0) {
+    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
+    if (!masked) exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
+  }
+  {
+    const dim3 grid((unsigned)B, CH);
+    if (masked) {
+      if (dj.greedy) sample_partial_kernel<DT, true, true><<<grid, PT, 0, st>>>(dj, ws);
+      else sample_partial_kernel<DT, true, false><<<grid, PT, 0, st>>>(dj, ws);
+    } else {
+      if (dj.greedy) sample_partial_kernel<DT, false, true><<<grid, PT, 0, st>>>(dj, ws);
+      else sample_partial_kernel<DT, false, false><<<grid, PT, 0, st>>>(dj, ws);
+    }
+  }
+  sample_final_kernel<DT><<<B, NT, 0, st>>>(dj, ws);
+  if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+  return cudaGetLastError();
+}
+
 #define DISPATCH_DT(dtype, ...)                                          \
   switch (dtype) {                                                       \
     case SPECDEC_F32: { constexpr int DT = DT_F32; __VA_ARGS__; } break;   \
@@ -808,6 +908,11 @@ const char* specdec_error_string(int code) {
 
 size_t specdec_workspace_bytes(int64_t rows) { return (size_t)(rows < 0 ? 0 : rows) * (sizeof(RowOut) + 16) + 256; }
 
+size_t specdec_verify_workspace_bytes(int B, int gamma, int V) {
+  if (B <= 0 || gamma < 0 || V <= 0) return 256;
+  return ws_layout(B, gamma, V, (long long)B * (2 * gamma + 1)).total + 256;
+}
+
 int specdec_verify(const void* target_logits, const void* draft_logits, int dtype, const int64_t* draft_tokens,
                    const float* u_accept, const float* u_sample, uint64_t philox_seed, uint64_t philox_offset,
                    int64_t seq_id0, int B, int gamma, int V, int64_t stride_tb, int64_t stride_tg, int64_t stride_db,
@@ -827,8 +932,11 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
   const int nD = ngram ? 0 : gamma;
   if (nT + nD == 0) return SPECDEC_ERR_ARG;
   DecideJob dj;
+  const long long R = (long long)B * (nT + nD);
+  const WsLayout wl = ws_layout(B, gamma, V, R);
+  if (workspace_bytes < wl.total) return SPECDEC_ERR_WORKSPACE;
   int rc = fill_rowjob(dj.rj, target_logits, draft_logits, stride_tb, stride_tg, stride_db, stride_dg, nT, nD, V,
-                       temperature, top_k, top_p, (long long)B * (nT + nD), workspace, workspace_bytes);
+                       temperature, top_k, top_p, R, workspace, workspace_bytes);
   if (rc) return rc;
   dj.draft_tokens = (const long long*)draft_tokens; dj.u_accept = u_accept; dj.u_sample = u_sample;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = gamma;
@@ -838,16 +946,23 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
   dj.q_tok = q_tok; dj.first_stop = first_stop; dj.next_prob = next_prob; dj.packed = packed;
   dj.lane_sample = 0x10000;
   cudaStream_t st = (cudaStream_t)stream;
-  if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+  if (ngram) {  // per-position sample(p_i) comparisons: exact statistics for every row, one CTA per sequence
+    if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+    DISPATCH_DT(dtype, {
+      cudaError_t e = launch_rowstats<DT>(dj.rj, st);
+      if (e != cudaSuccess) return (int)e;
+      if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+      decide_kernel<DT><<<B, NT, 0, st>>>(dj);
+      e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    });
+    if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+    return 0;
+  }
   DISPATCH_DT(dtype, {
-    cudaError_t e = launch_rowstats<DT>(dj.rj, st);
-    if (e != cudaSuccess) return (int)e;
-    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
-    decide_kernel<DT><<<B, NT, 0, st>>>(dj);
-    e = cudaGetLastError();
+    cudaError_t e = launch_hybrid<DT>(dj, wl, workspace, B, st);
     if (e != cudaSuccess) return (int)e;
   });
-  if (g_ev[2]) cudaEventRecord(g_ev[2], st);
   return 0;
 }
 
@@ -886,13 +1001,14 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
   if (rows > 0x7fffffff) return SPECDEC_ERR_RANGE;
   if (sample_mode != SPECDEC_SAMPLE_GREEDY && sample_mode != SPECDEC_SAMPLE_INVCDF) return SPECDEC_ERR_ARG;
   // a verify step with gamma = 0: every sequence "accepts all" and draws its bonus token
-  const size_t need = (size_t)rows * sizeof(RowOut) + (size_t)rows * (sizeof(int) * 2);
+  const WsLayout wl = ws_layout(rows, 0, V, rows);
+  const size_t need = wl.total + (size_t)rows * (sizeof(int) * 2);
   if (workspace_bytes < need) return SPECDEC_ERR_WORKSPACE;
   DecideJob dj;
   int rc = fill_rowjob(dj.rj, logits, nullptr, stride, 0, 0, 0, 1, 0, V, temperature, top_k, top_p, rows, workspace,
                        workspace_bytes);
   if (rc) return rc;
-  int* scratch = (int*)((char*)workspace + (size_t)rows * sizeof(RowOut));
+  int* scratch = (int*)((char*)workspace + wl.total);
   dj.draft_tokens = nullptr; dj.u_accept = nullptr; dj.u_sample = u;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = 0;
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = 0; dj.stop = nullptr; dj.n_stop = 0;
@@ -901,13 +1017,15 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
   dj.lane_sample = 0x20000 + lane_id;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_DT(dtype, {
-    cudaError_t e = launch_rowstats<DT>(dj.rj, st);
-    if (e != cudaSuccess) return (int)e;
-    decide_kernel<DT><<<(int)rows, NT, 0, st>>>(dj);
-    e = cudaGetLastError();
+    cudaError_t e = launch_hybrid<DT>(dj, wl, workspace, (int)rows, st);
     if (e != cudaSuccess) return (int)e;
   });
   return 0;
+}
+
+size_t specdec_sample_rows_workspace_bytes(int64_t rows, int V) {
+  if (rows <= 0 || V <= 0) return 256;
+  return ws_layout(rows, 0, V, rows).total + (size_t)rows * 8 + 256;
 }
 
 int specdec_sample_probs(const float* probs, int64_t rows, int V, int sample_mode, const float* u, int64_t* tok,

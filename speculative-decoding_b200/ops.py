@@ -82,7 +82,7 @@ def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_token
     nprob = torch.empty(B, dtype=torch.float32, device=dev)
     packed = torch.empty((B, gamma + 2), dtype=torch.int32, device=dev)
     lib = L.lib()
-    ws_bytes = lib.specdec_workspace_bytes(B * (2 * gamma + 1))
+    ws_bytes = lib.specdec_verify_workspace_bytes(B, gamma, V)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     sd = draft_logits.stride() if draft_logits is not None else (0, 0, 1)
     with torch.cuda.device(dev):
@@ -144,7 +144,7 @@ def sample_rows_op(logits: Tensor, u: Optional[Tensor], seed: int, offset: int, 
     tok = torch.empty(rows, dtype=torch.int64, device=dev)
     ptok = torch.empty(rows, dtype=torch.float32, device=dev)
     lib = L.lib()
-    ws_bytes = lib.specdec_workspace_bytes(rows)
+    ws_bytes = lib.specdec_sample_rows_workspace_bytes(rows, V)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     with torch.cuda.device(dev):
         rc = lib.specdec_sample_rows(_ptr(x), _dtype_code(x), rows, V, stride, float(temperature), int(top_k),
