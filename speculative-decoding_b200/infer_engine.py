@@ -35,7 +35,6 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
     n_gen = torch.zeros(B, dtype=torch.long, device=device)
     n_acc = torch.zeros(B, dtype=torch.long, device=device)
     end_tokens = torch.as_tensor(list(ctx.end_tokens), dtype=torch.long, device=device)
-    ar = torch.arange(ctx.gamma, device=device)
 
     out0 = ctx.drafter(input_ids, attention_mask=attention_mask, use_cache=True)
     drafter_past = out0.past_key_values
@@ -90,7 +89,7 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
         rejected = (~hit_end) & (n < g)
         n_acc += torch.where(active, acc_cnt, torch.zeros_like(acc_cnt))
         # corrected token at step+n, zeros after it (:326,:333-336)
-        pos = step + ar.unsqueeze(0)                                   # [1,g]
+        ar = torch.arange(g, device=device)
         cur = generated[:, step:step + g]
         corr = rejected.unsqueeze(1) & (ar.unsqueeze(0) == n.unsqueeze(1))
         cur = torch.where(corr, x.unsqueeze(1), cur)
@@ -100,7 +99,6 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
         x_is_end = torch.isin(x, end_tokens) if end_tokens.numel() else torch.zeros_like(rejected)
         finished = finished | (active & (hit_end | (rejected & x_is_end)))
         step += g
-        del pos
 
     outs: List[torch.Tensor] = []
     rates: List[float] = []
