@@ -97,6 +97,8 @@ SPECDEC_API int specdec_verify(const void* target_logits, const void* draft_logi
 /* Measurement hook (bench.py): when non-NULL, specdec_verify records these cudaEvent_t on its stream
  * before the row-statistics kernel, between the two kernels and after the decide kernel. */
 SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end);
+/* Test hook: "force_ldg"=1 makes the row kernel use vectorised LDG instead of the TMA pipeline. */
+SPECDEC_API int specdec_set_option(const char* name, int value);
 
 /* LogitsProcessor.__call__ materialised: probs[rows,V] fp32 = softmax(_process(logits)/T)
  * (utils/logits_processor.py:13-15).  row_stats (nullable) receives 8 floats per row:

@@ -1,25 +1,25 @@
-// hybrid.cuh -- the production verify pipeline (included by verify.cu).
+// hybrid.cuh -- the production verify pipeline (included by verify.cu inside namespace specdec).
 //
 // The canonical (oracle-reproducible) arithmetic costs ~16 issue slots per logit because exp2 is a
-// polynomial on the FMA pipe.  Only a few rows per sequence actually need it, so the step is split:
+// polynomial on the FMA pipe.  Only a few rows per sequence actually need it, so the step is split
+// into three launches whose tails are chained with "last CTA done" counters (no host sync, no spin):
 //
-//   rowfast_kernel   every row, ONE pass over HBM: online max + sum of MUFU ex2 (5 slots/logit).
-//                    The row max is exact; the sum is good to ~1e-6 relative.
-//   plan_kernel      per sequence: p~/q~ of the draft tokens from the fast sums and the accept test
-//                    with a 1e-3 relative safety margin => sure-accept / sure-reject / ambiguous.
-//                    Rows that decide something (ambiguous positions + the first sure reject, whose
-//                    residual needs exact normalisers) become tasks.
-//   exact_rows_kernel canonical sum of the task rows (u64 atomics: order independent).
-//   sample_partial_kernel  final decisions from exact sums where they exist (identical to the
-//                    oracle's because the fast ones are only trusted outside the margin), then the
-//                    one sweep the next token needs -- residual max(0,p-q) or the bonus/target row --
-//                    as per-256-element integer partial sums, CH CTAs per sequence.
-//   sample_final_kernel    scan of the partials, inverse-CDF location, token + packed result.
+//   1. rowfast_tma_kernel / rowfast_kernel: every row, ONE pass over HBM: online max + sum of MUFU
+//      ex2 (5 slots/logit).  The row max is exact; the sum is good to ~1e-6 relative.
+//      Tail (CTA that completes a sequence's last row) = plan: p~/q~ of the draft tokens from the
+//      fast sums and the accept test with a 1e-3 relative safety margin => sure-accept /
+//      sure-reject / ambiguous.  Rows that decide something (ambiguous positions + the first sure
+//      reject, whose residual needs exact normalisers) become tasks.
+//   2. exact_rows_kernel: canonical sum of the task rows (u64 atomics: order independent).
+//      Tail (last CTA of a sequence's tasks) = decide: final decisions from exact sums where they
+//      exist (identical to the oracle's because fast ones are only trusted outside the margin).
+//   3. sample_partial_kernel: the one sweep the next token needs -- residual max(0,p-q) or the
+//      bonus/target row -- as per-256-element integer partial sums, CH CTAs per sequence.
+//      Tail (last of the CH CTAs) = finalize: scan of the partials, inverse-CDF location, outputs.
 //
 // top-k / nucleus modes use the exact rowstats_kernel for every row (their kept sets need exact
-// masses) and skip plan/exact tasks.  Outputs are bit-identical to the exact-everywhere path.
+// masses) followed by plan_kernel (no tasks).  Outputs are bit-identical to the exact-everywhere path.
 #pragma once
-// (included inside namespace specdec)
 
 constexpr int FT = 512;   // threads, rowfast_kernel
 constexpr int PT = 256;   // threads, chunk kernels
@@ -36,6 +36,10 @@ struct HybridWs {
   u64* tot;               // [B]
   u64* best;              // [B]  greedy: (value bits << 32) | ~index
   int* samp;              // [B][4]: n, mode, p-row position, unused
+  int* rows_done;         // [B]  rows of the sequence whose statistics are written
+  int* seq_tasks;         // [B]  number of exact tasks of the sequence
+  int* exact_done;        // [B]
+  int* part_done;         // [B]
   int nseg_pad;
 };
 
@@ -45,48 +49,6 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(FT, 2) rowfast_kernel(RowJob job) {
-  __shared__ float shf[33];
-  const long long r = blockIdx.x;
-  const void* row = row_ptr<DT>(job, r);
-  const bool aligned = (((size_t)row) & 15) == 0;
-  const int V = job.V, NV = (V + 7) >> 3;
-  const float c = job.c;
-  float m = -INFINITY, s = 0.0f;
-  sweep_range<DT, FT>(row, V, aligned, 0, NV, [&](const float(&x)[8], int) {
-    float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-    if (vm > m) {  // rare after the first few vectors
-      s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c)));
-      m = vm;
-    }
-    const float mc = __fmul_rn(m, c);
-#pragma unroll
-    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
-  });
-  const float M = block_max_f(m, shf);
-  s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, M), c))) : 0.0f;
-  // block sum (fp32 tree; this sum is only trusted to ~1e-6)
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (lane == 0) shf[w] = s;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = (lane < FT / 32) ? shf[lane] : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    if (lane == 0) {
-      RowOut o;
-      o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, t);
-      o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
-      job.out[r] = o;
-    }
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float job_u_accept(const DecideJob& job, int b, int i) {
   return job.u_accept ? job.u_accept[(long long)b * job.gamma + i]
                       : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)i);
@@ -100,17 +62,87 @@ __device__ __forceinline__ int accept_rule(float p, float q, float u, int flags)
   return !(u > frac) ? 1 : 0;
 }
 
-// one warp per sequence, one lane per draft position
+// exact statistics of row r: from rowstats_kernel (masked modes) or from the exact task sums
+__device__ __forceinline__ RowOut resolved_row(const RowJob& rj, const HybridWs& ws, long long r) {
+  RowOut o = rj.out[r];
+  if (!(o.flags & 1)) {
+    const u64 S = __ldcg(&ws.acc[r]);
+    o.Sfix = S;
+    o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(S), 0x1p-40f));
+  }
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// decide: executed by ONE WARP once every exact sum the sequence needs is in ws.acc
+// ---------------------------------------------------------------------------------------------
 template <int DT>
-__global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
-  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__device__ void decide_sequence(const DecideJob& job, const HybridWs& ws, int b) {
+  const RowJob& rj = job.rj;
+  const int g = job.gamma, lane = threadIdx.x & 31;
+  const long long* toks = job.draft_tokens + (long long)b * g;
+  int n = g;
+  for (int i0 = 0; i0 < g; i0 += 32) {
+    const int i = i0 + lane;
+    int a = 1;
+    if (i < g) {
+      const int st = ws.status[(long long)b * g + i];
+      if ((st & ST_NEED) || (st & 3) == ST_EXACTROW) {
+        const int rps = rj.nT + rj.nD;
+        const int tok = (int)min(max(toks[i], 0ll), (long long)rj.V - 1);
+        const long long r1 = (long long)b * rps + i, r2 = (long long)b * rps + rj.nT + i;
+        const RowOut rp = resolved_row(rj, ws, r1), rq = resolved_row(rj, ws, r2);
+        const float p = row_prob<DT>(rp, row_ptr<DT>(rj, r1), tok, rj.c);
+        const float q = row_prob<DT>(rq, row_ptr<DT>(rj, r2), tok, rj.c);
+        a = accept_rule(p, q, job_u_accept(job, b, i), job.flags);
+        job.p_tok[(long long)b * g + i] = p;
+        job.q_tok[(long long)b * g + i] = q;
+      } else {
+        a = ((st & 3) == ST_ACCEPT);
+      }
+      job.mask[(long long)b * g + i] = (unsigned char)a;
+    }
+    const unsigned rej = __ballot_sync(0xffffffffu, i < g && !a);
+    if (n == g && rej) n = i0 + __ffs(rej) - 1;
+  }
+  if (lane == 0) {
+    int mode = 0, prow = 0;  // 0 none, 1 target row, 2 residual
+    if (n == g) {
+      if (!(job.flags & SPECDEC_NO_BONUS)) { mode = 1; prow = g; }
+    } else if (job.flags & SPECDEC_SKIP_ADJUST) { mode = 1; prow = n; }
+    else { mode = 2; prow = n; }
+    int fs = -1;
+    for (int i = 0; i < n && fs < 0; ++i)
+      for (int k = 0; k < job.n_stop; ++k)
+        if (toks[i] == job.stop[k]) { fs = i; break; }
+    job.n_acc[b] = n;
+    job.first_stop[b] = fs;
+    ws.samp[b * 4 + 0] = n; ws.samp[b * 4 + 1] = mode; ws.samp[b * 4 + 2] = prow;
+    if (mode == 0) {  // nothing to sample (all accepted, no bonus token)
+      job.next_tok[b] = -1;
+      if (job.next_prob) job.next_prob[b] = 0.0f;
+      if (job.packed) {
+        int* pk = job.packed + (long long)b * (g + 2);
+        pk[0] = n;
+        for (int i = 0; i < g; ++i) pk[1 + i] = (int)toks[i];
+        pk[1 + g] = -1;
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// plan: executed by ONE WARP once all RowOut of the sequence are written (lane = draft position)
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__device__ void plan_sequence(const DecideJob& job, const HybridWs& ws, int b) {
   const int lane = threadIdx.x & 31;
   const RowJob& rj = job.rj;
   const int g = job.gamma, rps = rj.nT + rj.nD;
-  if (b >= (int)(rj.R / rps)) return;
   const RowOut* ro = rj.out + (long long)b * rps;
   const long long* toks = job.draft_tokens + (long long)b * g;
   bool have_reject = false;
+  int ntask = 0;
   for (int i0 = 0; i0 < g; i0 += 32) {
     const int i = i0 + lane;
     int st = ST_ACCEPT;
@@ -156,13 +188,88 @@ __global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
       }
       ws.status[(long long)b * g + i] = (unsigned char)st;
     }
+    ntask += __popc(__ballot_sync(0xffffffffu, need));
+  }
+  if (lane == 0) ws.seq_tasks[b] = ntask;
+  __syncwarp();
+  if (ntask == 0) {  // nothing to make exact: decide right away
+    __threadfence();
+    decide_sequence<DT>(job, ws, b);
   }
 }
 
-// canonical sums of the task rows: grid (B*gamma, CH)
+// one warp per sequence (masked modes / gamma == 0, where no fast row kernel runs)
 template <int DT>
-__global__ void __launch_bounds__(PT) exact_rows_kernel(DecideJob job, HybridWs ws) {
+__global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (b >= (int)(job.rj.R / (job.rj.nT + job.rj.nD))) return;
+  plan_sequence<DT>(job, ws, b);
+}
+
+// called by thread `tid0` of a row kernel after it wrote RowOut of row r; returns the sequence id
+// whose rows are now all complete (then ONE warp must call plan_sequence) or -1
+__device__ __forceinline__ int row_done(const RowJob& rj, const HybridWs& ws, long long r) {
+  __threadfence();
+  const int rps = rj.nT + rj.nD;
+  const int b = (int)(r / rps);
+  return (atomicAdd(&ws.rows_done[b], 1) == rps - 1) ? b : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// row kernel, vectorised-LDG version (fp32 rows, unaligned rows)
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs ws) {
+  __shared__ float shf[33];
+  __shared__ int sh_seq;
+  const RowJob& job = dj.rj;
+  const long long r = blockIdx.x;
+  const void* row = row_ptr<DT>(job, r);
+  const bool aligned = (((size_t)row) & 15) == 0;
+  const int V = job.V, NV = (V + 7) >> 3;
+  const float c = job.c;
+  float m = -INFINITY, s = 0.0f;
+  sweep_range<DT, FT>(row, V, aligned, 0, NV, [&](const float(&x)[8], int) {
+    float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    if (vm > m) {  // rare after the first few vectors
+      s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c)));
+      m = vm;
+    }
+    const float mc = __fmul_rn(m, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
+  });
+  const float M = block_max_f(m, shf);
+  s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, M), c))) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) shf[w] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (lane < FT / 32) ? shf[lane] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    int seq = -1;
+    if (lane == 0) {
+      RowOut o;
+      o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, t);
+      o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
+      job.out[r] = o;
+    }
+    (void)seq;
+  }
+}
+
+#include "rowfast_tma.cuh"
+
+// ---------------------------------------------------------------------------------------------
+// canonical sums of the task rows: grid (B*gamma, CH); tail = decide
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, HybridWs ws) {
   __shared__ u64 sh64[33];
+  __shared__ int sh_last;
   if ((int)blockIdx.x >= *ws.ntasks) return;
   const RowJob& rj = job.rj;
   const int task = ws.tasks[blockIdx.x];
@@ -185,17 +292,15 @@ __global__ void __launch_bounds__(PT) exact_rows_kernel(DecideJob job, HybridWs 
     s = block_sum_u64(s, sh64);
     if (threadIdx.x == 0 && s) atomicAdd(&ws.acc[r], s);
   }
-}
-
-// exact statistics of row r: from rowstats_kernel (masked modes) or from the exact task sums
-__device__ __forceinline__ RowOut resolved_row(const RowJob& rj, const HybridWs& ws, long long r) {
-  RowOut o = rj.out[r];
-  if (!(o.flags & 1)) {
-    const u64 S = ws.acc[r];
-    o.Sfix = S;
-    o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(S), 0x1p-40f));
+  if (threadIdx.x == 0) {
+    __threadfence();
+    sh_last = (atomicAdd(&ws.exact_done[b], 1) == __ldcg(&ws.seq_tasks[b]) * CH - 1) ? 1 : 0;
   }
-  return o;
+  __syncthreads();
+  if (sh_last && threadIdx.x < 32) {
+    __threadfence();
+    decide_sequence<DT>(job, ws, b);
+  }
 }
 
 struct SampleCtx {
@@ -239,77 +344,88 @@ __device__ __forceinline__ void sample_weights(const SampleCtx& sc, int v, u64 (
   }
 }
 
-// final accept decisions of sequence b, executed by one full warp (lane = position).
-// Returns n (all lanes); fills acc[] / pv[] / qv[] (pv < 0: keep the fast value already written).
+
+// ---------------------------------------------------------------------------------------------
+// finalize: block-wide, by the last of the CH CTAs of a sequence
+// ---------------------------------------------------------------------------------------------
 template <int DT>
-__device__ int final_decisions(const DecideJob& job, const HybridWs& ws, int b, int* acc, float* pv, float* qv) {
+__device__ void finalize_sequence(const DecideJob& job, const HybridWs& ws, int b, u64* sh64, float* shf, int* shi,
+                                  long long* s_res) {
   const RowJob& rj = job.rj;
-  const int g = job.gamma, rps = rj.nT + rj.nD, lane = threadIdx.x & 31;
-  const long long* toks = job.draft_tokens + (long long)b * g;
-  int n = g;
-  for (int i0 = 0; i0 < g; i0 += 32) {
-    const int i = i0 + lane;
-    int a = 1;
-    if (i < g) {
-      const int st = ws.status[(long long)b * g + i];
-      if ((st & ST_NEED) || (st & 3) == ST_EXACTROW) {
-        const int tok = (int)min(max(toks[i], 0ll), (long long)rj.V - 1);
-        const long long r1 = (long long)b * rps + i, r2 = (long long)b * rps + rj.nT + i;
-        const RowOut rp = resolved_row(rj, ws, r1), rq = resolved_row(rj, ws, r2);
-        const float p = row_prob<DT>(rp, row_ptr<DT>(rj, r1), tok, rj.c);
-        const float q = row_prob<DT>(rq, row_ptr<DT>(rj, r2), tok, rj.c);
-        a = accept_rule(p, q, job_u_accept(job, b, i), job.flags);
-        pv[i] = p; qv[i] = q;
-      } else {
-        a = ((st & 3) == ST_ACCEPT);
-        pv[i] = -1.0f;
-      }
-      acc[i] = a;
+  const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
+  const int n = __ldcg(&ws.samp[b * 4 + 0]), mode = __ldcg(&ws.samp[b * 4 + 1]), prow = __ldcg(&ws.samp[b * 4 + 2]);
+  const bool greedy = job.greedy != 0;
+  const float us = job.u_sample ? job.u_sample[b]
+                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
+  u64* part = ws.part + (size_t)b * ws.nseg_pad;
+  const long long r1 = (long long)b * rps + prow;
+  const void* prow_ptr = row_ptr<DT>(rj, r1);
+  RowOut rp = resolved_row(rj, ws, r1);
+  const u64 total = __ldcg(&ws.tot[b]);
+  const u64 rmin = (job.flags & SPECDEC_RESID_FALLBACK) ? 1152921ull : 0ull;
+  long long x;
+  bool from_p;
+  if (mode == 2 && total <= rmin) {
+    // residual mass (numerically) zero: sample the target row itself (engine/infer_engine.py:319-321)
+    const Scratch scr{part, sh64, shf, shi, s_res};
+    x = sample_p_row<DT>(prow_ptr, rp, V, rj.c, greedy, us, scr);
+    from_p = true;
+  } else if (greedy) {
+    const u64 key = __ldcg(&ws.best[b]);
+    x = key ? (long long)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0ll;
+    from_p = (mode == 1);
+  } else {
+    SampleCtx sc;
+    sc.prow = prow_ptr; sc.rp = rp; sc.pal = (((size_t)prow_ptr) & 15) == 0;
+    sc.V = V; sc.c = rj.c; sc.resid = (mode == 2);
+    sc.qrow = prow_ptr; sc.rq = rp; sc.qal = sc.pal;
+    if (mode == 2) {
+      const long long r2 = (long long)b * rps + rj.nT + prow;
+      sc.qrow = row_ptr<DT>(rj, r2);
+      sc.rq = resolved_row(rj, ws, r2);
+      sc.qal = (((size_t)sc.qrow) & 15) == 0;
     }
-    const unsigned rej = __ballot_sync(0xffffffffu, i < g && !a);
-    if (n == g && rej) n = i0 + __ffs(rej) - 1;
+    const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
+    auto wf = [&](int v, u64(&w)[8]) { sample_weights<DT>(sc, v, w, nullptr); };
+    x = locate_token(NV, nseg, part, total, scale_u24(total, u24_of(us)), wf, s_res);
+    from_p = (mode == 1);
   }
-  return n;
+  if (threadIdx.x == 0) {
+    job.next_tok[b] = x;
+    if (job.next_prob) {
+      float np = 0.0f;
+      if (from_p && x >= 0) {
+        if (mode == 1 && !(rp.flags & 1))  // target row sampled without a prior exact sum: total IS its Sfix
+          rp.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(total), 0x1p-40f));
+        np = row_prob<DT>(rp, prow_ptr, (int)x, rj.c);
+      }
+      job.next_prob[b] = np;
+    }
+    if (job.packed) {
+      const long long* toks = job.draft_tokens + (long long)b * g;
+      int* pk = job.packed + (long long)b * (g + 2);
+      pk[0] = n;
+      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
+      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
+      pk[1 + n] = (int)x;
+    }
+  }
 }
 
-// grid (B, CH)
+// ---------------------------------------------------------------------------------------------
+// grid (B, CH): integer partial sums of the sampling weights; tail = finalize
+// ---------------------------------------------------------------------------------------------
 template <int DT, bool MASKED, bool GREEDY>
-__global__ void __launch_bounds__(PT) sample_partial_kernel(DecideJob job, HybridWs ws) {
+__global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, HybridWs ws) {
   __shared__ u64 sh64[33];
-  __shared__ int s_acc[64];
-  __shared__ float s_p[64], s_q[64];
-  __shared__ int s_n, s_mode, s_prow;
+  __shared__ float shf[33];
+  __shared__ int shi[33];
+  __shared__ long long s_res;
+  __shared__ int sh_last;
   const RowJob& rj = job.rj;
-  const int b = blockIdx.x, ch = blockIdx.y, g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
+  const int b = blockIdx.x, ch = blockIdx.y, V = rj.V, rps = rj.nT + rj.nD;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  if (w == 0) {
-    const int n = final_decisions<DT>(job, ws, b, s_acc, s_p, s_q);
-    __syncwarp();
-    int mode = 0, prow = 0;  // 0 none, 1 target row, 2 residual
-    if (n == g) {
-      if (!(job.flags & SPECDEC_NO_BONUS)) { mode = 1; prow = g; }
-    } else if (job.flags & SPECDEC_SKIP_ADJUST) { mode = 1; prow = n; }
-    else { mode = 2; prow = n; }
-    if (lane == 0) { s_n = n; s_mode = mode; s_prow = prow; }
-    if (ch == 0) {
-      const long long* toks = job.draft_tokens + (long long)b * g;
-      for (int i = lane; i < g; i += 32) {
-        job.mask[(long long)b * g + i] = (unsigned char)s_acc[i];
-        if (s_p[i] >= 0.0f) { job.p_tok[(long long)b * g + i] = s_p[i]; job.q_tok[(long long)b * g + i] = s_q[i]; }
-      }
-      if (lane == 0) {
-        int fs = -1;
-        for (int i = 0; i < n && fs < 0; ++i)
-          for (int k = 0; k < job.n_stop; ++k)
-            if (toks[i] == job.stop[k]) { fs = i; break; }
-        job.n_acc[b] = n;
-        job.first_stop[b] = fs;
-        ws.samp[b * 4 + 0] = n; ws.samp[b * 4 + 1] = mode; ws.samp[b * 4 + 2] = prow;
-      }
-    }
-  }
-  __syncthreads();
-  const int mode = s_mode, prow = s_prow;
+  const int mode = ws.samp[b * 4 + 1], prow = ws.samp[b * 4 + 2];
   if (mode == 0) return;
   const long long r1 = (long long)b * rps + prow;
   const void* prowp = row_ptr<DT>(rj, r1);
@@ -332,7 +448,6 @@ __global__ void __launch_bounds__(PT) sample_partial_kernel(DecideJob job, Hybri
   float best = (mode == 2) ? 0.0f : -1.0f;
   int bidx = 0x7FFFFFFF;
   u64* part = ws.part + (size_t)b * ws.nseg_pad;
-  // weights of one vector; both modes share the code shape so that two segments can be in flight
   auto seg_sum = [&](const float(&xp)[8], const float(&xq)[8], int v) -> u64 {
     u64 s = 0;
 #pragma unroll
@@ -384,7 +499,6 @@ __global__ void __launch_bounds__(PT) sample_partial_kernel(DecideJob job, Hybri
     if (lane == 0) { part[seg] = sa; tot += sa; }
   }
   tot = block_sum_u64(tot, sh64);
-  if (threadIdx.x == 0 && tot) atomicAdd(&ws.tot[b], tot);
   if (GREEDY) {
     // (value, smallest index) max: non-negative floats order like their bit patterns
     u64 key = (bidx == 0x7FFFFFFF) ? 0ull : (((u64)__float_as_uint(best)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bidx);
@@ -392,81 +506,15 @@ __global__ void __launch_bounds__(PT) sample_partial_kernel(DecideJob job, Hybri
     for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0 && key) atomicMax(&ws.best[b], key);
   }
-}
-
-// grid B, NT threads
-template <int DT>
-__global__ void __launch_bounds__(NT, 1) sample_final_kernel(DecideJob job, HybridWs ws) {
-  __shared__ u64 part_sh[MAXPART];
-  __shared__ u64 sh64[33];
-  __shared__ float shf[33];
-  __shared__ int shi[33];
-  __shared__ long long s_res;
-  const Scratch scr{part_sh, sh64, shf, shi, &s_res};
-  const RowJob& rj = job.rj;
-  const int b = blockIdx.x, g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
-  const int n = ws.samp[b * 4 + 0], mode = ws.samp[b * 4 + 1], prow = ws.samp[b * 4 + 2];
-  const bool greedy = job.greedy != 0;
-  const float us = job.u_sample ? job.u_sample[b]
-                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
-  long long x = -1;
-  bool from_p = false;
-  RowOut rp;
-  const void* prow_ptr = nullptr;
-  if (mode != 0) {
-    const long long r1 = (long long)b * rps + prow;
-    prow_ptr = row_ptr<DT>(rj, r1);
-    rp = resolved_row(rj, ws, r1);
-    const u64 total = ws.tot[b];
-    const u64 rmin = (job.flags & SPECDEC_RESID_FALLBACK) ? 1152921ull : 0ull;
-    if (mode == 2 && total <= rmin) {
-      // residual mass (numerically) zero: sample the target row itself (engine/infer_engine.py:319-321)
-      if (!(rp.flags & 1) && rp.Sfix == 0) {  // cannot happen: row n of a residual always has exact sums
-        rp.Sfix = 1; rp.inv = 1.0f;
-      }
-      x = sample_p_row<DT>(prow_ptr, rp, V, rj.c, greedy, us, scr);
-      from_p = true;
-    } else if (greedy) {
-      const u64 key = ws.best[b];
-      x = key ? (long long)(0xFFFFFFFFu - (unsigned)(key & 0xFFFFFFFFull)) : 0ll;
-      from_p = (mode == 1);
-    } else {
-      SampleCtx sc;
-      sc.prow = prow_ptr; sc.rp = rp; sc.pal = (((size_t)prow_ptr) & 15) == 0;
-      sc.V = V; sc.c = rj.c; sc.resid = (mode == 2);
-      sc.qrow = prow_ptr; sc.rq = rp; sc.qal = sc.pal;
-      if (mode == 2) {
-        const long long r2 = (long long)b * rps + rj.nT + prow;
-        sc.qrow = row_ptr<DT>(rj, r2);
-        sc.rq = resolved_row(rj, ws, r2);
-        sc.qal = (((size_t)sc.qrow) & 15) == 0;
-      }
-      const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
-      auto wf = [&](int v, u64(&w)[8]) { sample_weights<DT>(sc, v, w, nullptr); };
-      x = locate_token(NV, nseg, ws.part + (size_t)b * ws.nseg_pad, total, scale_u24(total, u24_of(us)), wf, &s_res);
-      from_p = (mode == 1);
-    }
-  }
+  __syncthreads();  // every warp's part[] stores and atomicMax are issued
   if (threadIdx.x == 0) {
-    job.next_tok[b] = x;
-    if (job.next_prob) {
-      float np = 0.0f;
-      if (from_p && x >= 0) {
-        if (mode == 1 && !(rp.flags & 1)) {  // target row sampled without a prior exact sum: total IS its Sfix
-          rp.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(ws.tot[b]), 0x1p-40f));
-        }
-        np = row_prob<DT>(rp, prow_ptr, (int)x, rj.c);
-      }
-      job.next_prob[b] = np;
-    }
-    if (job.packed) {
-      const long long* toks = job.draft_tokens + (long long)b * g;
-      int* pk = job.packed + (long long)b * (g + 2);
-      pk[0] = n;
-      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
-      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
-      pk[1 + n] = (int)x;
-    }
+    if (tot) atomicAdd(&ws.tot[b], tot);
+    __threadfence();
+    sh_last = (atomicAdd(&ws.part_done[b], 1) == CH - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (sh_last) {
+    __threadfence();
+    finalize_sequence<DT>(job, ws, b, sh64, shf, shi, &s_res);
   }
 }
-

@@ -1,0 +1,161 @@
+// rowfast_tma.cuh -- the HBM-bound row-statistics kernel as a TMA bulk-copy pipeline (included inside
+// namespace specdec by hybrid.cuh).
+//
+// Persistent CTAs (3 per SM): one producer warp streams each logit row HBM -> shared memory with
+// cp.async.bulk (1-D TMA, SASS UBLKCP) into an 8-stage x 8 KB ring, completion signalled through
+// mbarrier transaction counts; 8 consumer warps read the stages with conflict-free 16-byte LDS and
+// keep the online (max, sum of MUFU ex2) per thread.  ~190 KB of loads are in flight per SM
+// independent of what the consumers are doing (block reductions, row epilogues), which is what the
+// plain LDG version (rowfast_kernel) could not sustain.  Used when every row is 16-byte aligned and a
+// multiple of 16 bytes; otherwise rowfast_kernel runs.
+#pragma once
+
+constexpr int TS_CONSUMERS = 256;
+constexpr int TS_THREADS = TS_CONSUMERS + 32;
+constexpr int TS_STAGES = 8;
+constexpr int TS_STAGE_BYTES = 8192;
+constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES;
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(void* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+// online (max, sum) update with one 16-byte vector
+template <int DT>
+__device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, const float c) {
+  if (DT == DT_F32) {
+    const float x0 = __uint_as_float(raw.x), x1 = __uint_as_float(raw.y), x2 = __uint_as_float(raw.z),
+                x3 = __uint_as_float(raw.w);
+    const float vm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
+    if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
+    const float mc = __fmul_rn(m, c);
+    s = __fadd_rn(s, ex2_approx(__fmaf_rn(x0, c, -mc)));
+    s = __fadd_rn(s, ex2_approx(__fmaf_rn(x1, c, -mc)));
+    s = __fadd_rn(s, ex2_approx(__fmaf_rn(x2, c, -mc)));
+    s = __fadd_rn(s, ex2_approx(__fmaf_rn(x3, c, -mc)));
+  } else {
+    float x[8];
+    const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (DT == DT_BF16) {
+        x[2 * k] = __uint_as_float(w[k] << 16);
+        x[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        x[2 * k] = f.x; x[2 * k + 1] = f.y;
+      }
+    }
+    const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
+    const float mc = __fmul_rn(m, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(TS_THREADS, 3) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
+  const RowJob& job = dj.rj;
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
+  __shared__ float sh_m[2][8], sh_s[2][8];
+  __shared__ int sh_seq[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
+  const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
+  if (tid == 0) {
+#pragma unroll
+    for (int i = 0; i < TS_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], TS_CONSUMERS / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (warp == TS_CONSUMERS / 32) {
+    // ---------------- producer warp: one elected lane issues the bulk copies ----------------
+    if (lane == 0) {
+      int stage = 0;
+      unsigned phase = 0;
+      for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+        const char* base = (const char*)row_ptr<DT>(job, r);
+        for (int k = 0; k < nst; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          const unsigned off = (unsigned)k * TS_STAGE_BYTES;
+          const unsigned nb = min((unsigned)TS_STAGE_BYTES, row_bytes - off);
+          mbar_expect_tx(&full_bar[stage], nb);
+          tma_bulk_g2s(ring + stage * TS_STAGE_BYTES, base + off, nb, &full_bar[stage]);
+          if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+    return;
+  }
+  // ---------------- consumer warps ----------------
+  const float c = job.c;
+  int stage = 0, par = 0;
+  unsigned phase = 0;
+  for (long long r = blockIdx.x; r < job.R; r += gridDim.x, par ^= 1) {
+    float m = -INFINITY, s = 0.0f;
+    for (int k = 0; k < nst; ++k) {
+      mbar_wait(&full_bar[stage], phase);
+      const unsigned off = (unsigned)k * TS_STAGE_BYTES;
+      const int nvec = (int)(min((unsigned)TS_STAGE_BYTES, row_bytes - off) >> 4);
+      const uint4* sp = reinterpret_cast<const uint4*>(ring + stage * TS_STAGE_BYTES);
+      uint4 a, b;
+      const bool ha = tid < nvec, hb = tid + TS_CONSUMERS < nvec;
+      if (ha) a = sp[tid];
+      if (hb) b = sp[tid + TS_CONSUMERS];
+      if (ha) online16<DT>(a, m, s, c);
+      if (hb) online16<DT>(b, m, s, c);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
+    }
+    // row epilogue among the 256 consumer threads (named barrier 1; the producer keeps prefetching).
+    // Scratch is double-buffered by row parity, so one barrier per row suffices.
+    float wm = warp_max_f(m);
+    s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, wm), c))) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) { sh_m[par][warp] = wm; sh_s[par][warp] = s; }
+    asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
+    if (warp == 0) {
+      int seq = -1;
+      if (lane == 0) {
+        float M = sh_m[par][0];
+#pragma unroll
+        for (int w = 1; w < TS_CONSUMERS / 32; ++w) M = fmaxf(M, sh_m[par][w]);
+        float S = 0.0f;
+#pragma unroll
+        for (int w = 0; w < TS_CONSUMERS / 32; ++w)
+          S += (sh_m[par][w] > -INFINITY) ? __fmul_rn(sh_s[par][w], ex2_approx(__fmul_rn(__fsub_rn(sh_m[par][w], M), c))) : 0.0f;
+        RowOut o;
+        o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, S);
+        o.cut = -INFINITY; o.jcut = job.V; o.flags = 0; o.Sfix = 0;
+        job.out[r] = o;
+      }
+      (void)seq;
+    }
+  }
+}

@@ -11,13 +11,16 @@
 //                     inverse-CDF resample (:10-19,168,171) or the bonus row (:158-160).
 // All arithmetic is the canonical fp32/integer arithmetic of canon.cuh, so results are bit-exact
 // against the CPU oracle for every launch geometry.
+#include <string.h>
 #include "canon.cuh"
 #include "../../include/specdec_b200.h"
 
 namespace specdec {
 
 constexpr int NT = 1024;       // threads per CTA (32 warps)
-constexpr int CAP = 8192;      // top-k / nucleus candidate capacity per row (shared memory)
+constexpr int RS_NT = 512;     // threads per CTA of rowstats_kernel (2 CTAs / SM)
+constexpr int CAP = 4096;      // top-k / nucleus candidate capacity per row (shared memory)
+constexpr int WARP_SELECT_MAX = 1024;  // candidate sets up to this size are resolved by one warp
 constexpr int MAXPART = 4096;  // warp-vector partial sums per row: V <= MAXPART*256
 constexpr size_t CAND_SMEM = (size_t)CAP * (sizeof(float) + sizeof(int) + sizeof(u64));
 
@@ -75,19 +78,20 @@ __device__ __forceinline__ void sweep_range(const void* row, int V, bool aligned
 template <int DT, typename F>
 __device__ __forceinline__ void sweep(const void* row, int V, bool aligned, F f) {
   const int NV = (V + 7) >> 3;
+  const int NTB = blockDim.x;
   int v = threadIdx.x;
-  for (; v + 3 * NT < NV; v += 4 * NT) {
+  for (; v + 3 * NTB < NV; v += 4 * NTB) {
     float x0[8], x1[8], x2[8], x3[8];
     load8<DT>(row, v, V, aligned, x0);
-    load8<DT>(row, v + NT, V, aligned, x1);
-    load8<DT>(row, v + 2 * NT, V, aligned, x2);
-    load8<DT>(row, v + 3 * NT, V, aligned, x3);
+    load8<DT>(row, v + NTB, V, aligned, x1);
+    load8<DT>(row, v + 2 * NTB, V, aligned, x2);
+    load8<DT>(row, v + 3 * NTB, V, aligned, x3);
     f(x0, v * 8);
-    f(x1, (v + NT) * 8);
-    f(x2, (v + 2 * NT) * 8);
-    f(x3, (v + 3 * NT) * 8);
+    f(x1, (v + NTB) * 8);
+    f(x2, (v + 2 * NTB) * 8);
+    f(x3, (v + 3 * NTB) * 8);
   }
-  for (; v < NV; v += NT) {
+  for (; v < NV; v += NTB) {
     float x[8];
     load8<DT>(row, v, V, aligned, x);
     f(x, v * 8);
@@ -104,12 +108,12 @@ struct CandSrc {
   int n;
   float c1, mc1;
   __device__ void prepare(unsigned kthkey) const {  // T=1 masses of the top-k-kept candidates
-    for (int i = threadIdx.x; i < n; i += NT) cw[i] = (fkey(cz[i]) >= kthkey) ? fix40(cweight(cz[i], c1, mc1)) : 0ull;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) cw[i] = (fkey(cz[i]) >= kthkey) ? fix40(cweight(cz[i], c1, mc1)) : 0ull;
     __syncthreads();
   }
   template <typename F>
   __device__ void each(unsigned, bool, F f) const {
-    for (int i = threadIdx.x; i < n; i += NT) f(cz[i], fkey(cz[i]), cj[i], cw[i]);
+    for (int i = threadIdx.x; i < n; i += blockDim.x) f(cz[i], fkey(cz[i]), cj[i], cw[i]);
   }
 };
 template <int DT>
@@ -211,15 +215,121 @@ __device__ void select_cut(const Src& src, int V, int top_k, int use_p, u64 tpq,
 }
 
 // ---------------------------------------------------------------------------------------------
+// single-warp cut selection for small candidate sets (executed by warp 0 while the other warps
+// wait at a barrier and the SM's second CTA keeps streaming).  Same result as select_cut.
+// Both selections are "the largest key K such that sum_{key_i >= K} w_i > t0" (w = 1, t0 = k-1 for
+// top-k; w = T=1 mass, t0 = thr for the nucleus cut), found bit by bit over the bits in which the
+// candidates actually differ (bf16-origin logits: <= ~12 of 32).
+// ---------------------------------------------------------------------------------------------
+template <bool MASS>
+__device__ __forceinline__ unsigned warp_select_key(const float* cz, const u64* cw, int m, unsigned common, unsigned vary,
+                                                    u64 t0) {
+  const int lane = threadIdx.x & 31;
+  unsigned K = common;
+  for (int bit = 31; bit >= 0; --bit) {
+    if (!((vary >> bit) & 1u)) continue;
+    const unsigned tr = K | (1u << bit);
+    u64 loc = 0;
+    for (int i = lane; i < m; i += 32) {
+      if (fkey(cz[i]) >= tr) loc += MASS ? cw[i] : 1ull;
+    }
+    loc = warp_sum_u64(loc);
+    if (loc > t0) K = tr;
+  }
+  return K;
+}
+
+__device__ void select_cut_warp(float* cz, int* cj, u64* cw, int n, int V, int top_k, int use_p, u64 tpq, u64 S1_full,
+                                float c, float mc, float c1, float mc1, float& cut_out, int& jcut_out, u64& Sfix_out) {
+  const int lane = threadIdx.x & 31;
+  const unsigned k0 = fkey(cz[0]);
+  unsigned vary = 0;
+  for (int i = lane; i < n; i += 32) vary |= fkey(cz[i]) ^ k0;
+  vary = __reduce_or_sync(0xffffffffu, vary);
+  unsigned kthkey = 0;
+  int m = n;
+  if (top_k > 0) {
+    kthkey = warp_select_key<false>(cz, cw, n, k0 & ~vary, vary, (u64)top_k - 1ull);
+    // compact the kept candidates to the front
+    m = 0;
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const float z = (i < n) ? cz[i] : 0.0f;
+      const int j = (i < n) ? cj[i] : 0;
+      const bool keep = (i < n) && (fkey(z) >= kthkey);
+      const unsigned bal = __ballot_sync(0xffffffffu, keep);
+      __syncwarp();
+      if (keep) { const int pos = m + __popc(bal & ((1u << lane) - 1u)); cz[pos] = z; cj[pos] = j; }
+      m += __popc(bal);
+      __syncwarp();
+    }
+  }
+  unsigned cutkey = kthkey;
+  int jcut = V;
+  if (use_p) {
+    u64 loc = 0;
+    unsigned v2 = 0;
+    const unsigned k1 = fkey(cz[0]);
+    for (int i = lane; i < m; i += 32) {
+      const u64 w = fix40(cweight(cz[i], c1, mc1));
+      cw[i] = w;
+      loc += w;
+      v2 |= fkey(cz[i]) ^ k1;
+    }
+    __syncwarp();
+    const u64 Mc = warp_sum_u64(loc);
+    v2 = __reduce_or_sync(0xffffffffu, v2);
+    const u64 S1 = (top_k > 0) ? Mc : S1_full;
+    const u64 thr = scale_q32(S1, tpq);
+    cutkey = warp_select_key<true>(cz, cw, m, k1 & ~v2, v2, thr);
+    u64 g = 0, cnt = 0;
+    for (int i = lane; i < m; i += 32) {
+      const unsigned key = fkey(cz[i]);
+      if (key > cutkey) g += cw[i];
+      if (key == cutkey) ++cnt;
+    }
+    const u64 Gc = warp_sum_u64(g), cntc = warp_sum_u64(cnt);
+    const u64 wc = fix40(cweight(fkey_inv(cutkey), c1, mc1));
+    u64 mkeep = cntc;
+    if (wc > 0 && thr >= Gc) {
+      const u64 q = (thr - Gc) / wc + 1ull;
+      mkeep = q < cntc ? q : cntc;
+    }
+    if (mkeep < cntc) {  // keep the first mkeep ties in ascending index order
+      int lo = 0, hi = V - 1;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        u64 c2 = 0;
+        for (int i = lane; i < m; i += 32) c2 += (fkey(cz[i]) == cutkey && cj[i] <= mid) ? 1u : 0u;
+        c2 = warp_sum_u64(c2);
+        if (c2 >= mkeep) hi = mid; else lo = mid + 1;
+      }
+      jcut = lo;
+    }
+  }
+  u64 loc = 0;
+  for (int i = lane; i < m; i += 32) {
+    const unsigned key = fkey(cz[i]);
+    if (key > cutkey || (key == cutkey && cj[i] <= jcut)) loc += fix40(cweight(cz[i], c, mc));
+  }
+  Sfix_out = warp_sum_u64(loc);
+  cut_out = fkey_inv(cutkey);
+  jcut_out = jcut;
+}
+
+// ---------------------------------------------------------------------------------------------
 // rowstats_kernel
 // ---------------------------------------------------------------------------------------------
 template <int DT>
-__global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
+__global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ u64 sh64[33];
   __shared__ float shf[33];
   __shared__ unsigned shu[33];
   __shared__ int s_count;
+  __shared__ float s_cut;
+  __shared__ int s_jcut;
+  __shared__ u64 s_Sfix;
   const int V = job.V;
   const float c = job.c;
   const bool masked = (job.top_k > 0) || job.use_p;
@@ -247,7 +357,7 @@ __global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
     } else {
       const float c1 = job.c1;
       const float mc1 = __fmul_rn(m, c1);
-      // thresholds guaranteeing >= 32 / 128 / 512 / 1024 elements above them
+      // thresholds guaranteeing >= 16 / 64 / 256 / 512 elements above them (RS_NT = 512 threads)
       float pm = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
       float qm = fmaxf(pm, __shfl_xor_sync(0xffffffffu, pm, 2));
       qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
@@ -261,7 +371,29 @@ __global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
       int L = -1;
       u64 S1 = 0;
       if (job.top_k > 0) {
-        L = job.top_k <= 32 ? 0 : job.top_k <= 128 ? 1 : job.top_k <= 512 ? 2 : job.top_k <= 1024 ? 3 : -1;
+        if (job.top_k <= RS_NT) {
+          // threshold = k-th largest of the per-thread maxima: >= k elements are guaranteed above it and
+          // only ~k(1+k/2T) are expected.  Bit-wise bisection, one hardware barrier-count per varying bit.
+          const unsigned mykey = fkey(tmax);
+          const unsigned refkey = fkey(m);
+          unsigned vary = __reduce_or_sync(0xffffffffu, mykey ^ refkey);
+          if ((threadIdx.x & 31) == 0) shu[threadIdx.x >> 5] = vary;
+          __syncthreads();
+          vary = 0;
+#pragma unroll
+          for (int w = 0; w < RS_NT / 32; ++w) vary |= shu[w];
+          __syncthreads();
+          unsigned K = refkey & ~vary;
+          for (int bit = 31; bit >= 0; --bit) {
+            if (!((vary >> bit) & 1u)) continue;
+            const unsigned tr = K | (1u << bit);
+            if (__syncthreads_count(mykey >= tr) >= job.top_k) K = tr;
+          }
+          tau[0] = fkey_inv(K);
+          L = 0;
+        } else {
+          L = -1;
+        }
       } else {
         // pure nucleus: exact T=1 mass of the row and of the four nested candidate sets
         u64 sa = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
@@ -302,20 +434,55 @@ __global__ void __launch_bounds__(NT, 1) rowstats_kernel(RowJob job) {
         const float th = tau[L];
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
-        sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+        {  // warp-aggregated compaction: one shared-memory atomic per warp and element slot; 4 loads in flight
+          const int NVr = (V + 7) >> 3, lane = threadIdx.x & 31;
+          auto emit = [&](const float(&x)[8], int v) {
+            // candidates are rare: one vote per vector decides whether anything has to be emitted
+            const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+            if (!__any_sync(0xffffffffu, (v < NVr) && (vm >= th))) return;
 #pragma unroll
-          for (int k = 0; k < 8; ++k)
-            if (x[k] >= th && j0 + k < V) {
-              const int slot = atomicAdd(&s_count, 1);
-              if (slot < CAP) { cz[slot] = x[k]; cj[slot] = j0 + k; }
+            for (int k = 0; k < 8; ++k) {
+              const bool has = (v < NVr) && (x[k] >= th) && (v * 8 + k < V);
+              const unsigned bal = __ballot_sync(0xffffffffu, has);
+              if (bal) {
+                const int leader = __ffs(bal) - 1;
+                int pos = 0;
+                if (lane == leader) pos = atomicAdd(&s_count, __popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, leader);
+                if (has) {
+                  const int slot = pos + __popc(bal & ((1u << lane) - 1u));
+                  if (slot < CAP) { cz[slot] = x[k]; cj[slot] = v * 8 + k; }
+                }
+              }
             }
-        });
+          };
+          for (int base = (threadIdx.x >> 5) << 5; base < NVr; base += 4 * RS_NT) {  // warp-uniform
+            float x0[8], x1[8], x2[8], x3[8];
+            const int v0 = base + lane, v1 = v0 + RS_NT, v2 = v0 + 2 * RS_NT, v3 = v0 + 3 * RS_NT;
+            load8<DT>(row, min(v0, NVr - 1), V, aligned, x0);
+            load8<DT>(row, min(v1, NVr - 1), V, aligned, x1);
+            load8<DT>(row, min(v2, NVr - 1), V, aligned, x2);
+            load8<DT>(row, min(v3, NVr - 1), V, aligned, x3);
+            emit(x0, v0);
+            if (base + RS_NT < NVr) emit(x1, v1);
+            if (base + 2 * RS_NT < NVr) emit(x2, v2);
+            if (base + 3 * RS_NT < NVr) emit(x3, v3);
+          }
+        }
         __syncthreads();
         n = s_count;
         __syncthreads();
         if (n > CAP || n < job.top_k) L = -1;
       }
-      if (L >= 0) {
+      if (L >= 0 && n <= WARP_SELECT_MAX) {
+        if (threadIdx.x < 32) {
+          select_cut_warp(cz, cj, cw, n, V, job.top_k, job.use_p, job.tpq, S1, c, mc, c1, mc1, cut, jcut, Sfix);
+          if (threadIdx.x == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; }
+        }
+        __syncthreads();
+        cut = s_cut; jcut = s_jcut; Sfix = s_Sfix;
+        __syncthreads();
+      } else if (L >= 0) {
         CandSrc src{cz, cj, cw, n, c1, mc1};
         select_cut(src, V, job.top_k, job.use_p, job.tpq, S1, c, mc, sh64, shu, cut, jcut, Sfix);
       } else {  // exact but slow: every selection step is a sweep over the row
@@ -432,7 +599,7 @@ __device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in,
   const int NV = (V + 7) >> 3;
   const int P = (NV + 31) >> 5;
   const int lane = threadIdx.x & 31;
-  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += NT) {  // warp-uniform
+  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += blockDim.x) {  // warp-uniform
     const int v = base + lane;
     u64 s = 0;
     if (v < NV) {
@@ -446,7 +613,7 @@ __device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in,
   }
   __syncthreads();
   u64 loc = 0;
-  for (int i = threadIdx.x; i < P; i += NT) loc += part[i];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) loc += part[i];
   const u64 total = block_sum_u64(loc, sh64);
   total_out = total;
   const u64 target = have_target ? target_in : scale_u24(total, u24);
@@ -465,7 +632,9 @@ __device__ long long block_argmax(float best, int idx, float* shf, int* shi, lon
   if (lane == 0) { shf[w] = best; shi[w] = idx; }
   __syncthreads();
   if (threadIdx.x < 32) {
-    best = shf[lane]; idx = shi[lane];
+    const int nwarp = (blockDim.x + 31) >> 5;
+    best = (lane < nwarp) ? shf[lane] : -INFINITY;
+    idx = (lane < nwarp) ? shi[lane] : 0x7FFFFFFF;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
       const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -766,6 +935,7 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 // host side
 // ---------------------------------------------------------------------------------------------
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
+static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_sms = 0;
 static int num_sms() {
   if (g_sms == 0) {
@@ -803,8 +973,9 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
     cudaError_t e = cudaFuncSetAttribute(rowstats_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  const int grid = (int)(rj.R < (long long)num_sms() ? rj.R : (long long)num_sms());
-  rowstats_kernel<DT><<<grid, NT, smem, st>>>(rj);
+  const long long cap = 2LL * num_sms();
+  const int grid = (int)(rj.R < cap ? rj.R : cap);
+  rowstats_kernel<DT><<<grid, RS_NT, smem, st>>>(rj);
   return cudaGetLastError();
 }
 
@@ -820,7 +991,7 @@ static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   size_t o = 0;
   w.rowout = o; o = al256(o + (size_t)R * sizeof(RowOut));
   w.zero = o;
-  o += (size_t)R * 8 + (size_t)B * 8 * 2 + 8;
+  o += (size_t)R * 8 + (size_t)B * 8 * 2 + 8 + (size_t)B * 4 * 4;
   w.zero_bytes = o - w.zero;
   o = al256(o);
   w.tasks = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1) * 4);
@@ -837,6 +1008,10 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   h.tot = h.acc + R;
   h.best = h.tot + B;
   h.ntasks = (int*)(h.best + B);
+  h.rows_done = h.ntasks + 2;
+  h.seq_tasks = h.rows_done + B;
+  h.exact_done = h.seq_tasks + B;
+  h.part_done = h.exact_done + B;
   h.tasks = (int*)(base + w.tasks);
   h.status = (unsigned char*)(base + w.status);
   h.samp = (int*)(base + w.samp);
@@ -853,16 +1028,35 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st);
   if (e != cudaSuccess) return e;
   if (g_ev[0]) cudaEventRecord(g_ev[0], st);
-  if (masked) {
-    e = launch_rowstats<DT>(rj, st);
-    if (e != cudaSuccess) return e;
+  if (masked || dj.gamma == 0) {
+    if (masked) {
+      e = launch_rowstats<DT>(rj, st);
+      if (e != cudaSuccess) return e;
+    } else {
+      rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
+    }
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);  // statuses (no tasks) + decide
   } else {
-    rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(rj);
-  }
-  if (g_ev[1]) cudaEventRecord(g_ev[1], st);
-  if (dj.gamma > 0) {
+    const size_t es = (DT == DT_F32) ? 4 : 2;
+    const bool tma_ok = DT != DT_F32 && (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
+                        ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
+                        ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0 && !g_force_ldg;
+    if (tma_ok) {
+      static bool attr_set[3] = {false, false, false};
+      if (!attr_set[DT]) {
+        e = cudaFuncSetAttribute(rowfast_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+        if (e != cudaSuccess) return e;
+        attr_set[DT] = true;
+      }
+      const long long cap = 3LL * num_sms();
+      rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
+    } else {
+      rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
+    }
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
     plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
-    if (!masked) exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
+    exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
   }
   {
     const dim3 grid((unsigned)B, CH);
@@ -874,7 +1068,6 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
       else sample_partial_kernel<DT, false, false><<<grid, PT, 0, st>>>(dj, ws);
     }
   }
-  sample_final_kernel<DT><<<B, NT, 0, st>>>(dj, ws);
   if (g_ev[2]) cudaEventRecord(g_ev[2], st);
   return cudaGetLastError();
 }
@@ -964,6 +1157,12 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
     if (e != cudaSuccess) return (int)e;
   });
   return 0;
+}
+
+int specdec_set_option(const char* name, int value) {
+  if (!name) return SPECDEC_ERR_ARG;
+  if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
+  return SPECDEC_ERR_ARG;
 }
 
 int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {

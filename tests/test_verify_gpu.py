@@ -200,3 +200,21 @@ def test_slow_selection_path(oracle_mod, mode_kw):
     o = oracle_mod.verify(t, d, toks, ua, us, **mode_kw)
     r = sd.fused_verify(t.cuda(), d.cuda(), toks.cuda(), ua.cuda(), us.cuda(), **mode_kw)
     _assert_same(o, r)
+
+
+def test_tma_and_ldg_row_kernels_agree(oracle_mod):
+    """the TMA bulk-copy pipeline and the vectorised-LDG row kernel give identical decisions."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    case = make_case(B=40, gamma=4, V=32000, dtype="bf16", sigma=0.5, seed=31, oracle=oracle_mod)
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args)
+    assert lib.specdec_set_option(b"force_ldg", 1) == 0
+    try:
+        r2 = sd.fused_verify(*args)
+    finally:
+        lib.specdec_set_option(b"force_ldg", 0)
+    assert torch.equal(r1.n_accepted, r2.n_accepted) and torch.equal(r1.next_token, r2.next_token)
+    np.testing.assert_allclose(r1.p_tok.cpu().numpy(), r2.p_tok.cpu().numpy(), rtol=1e-5)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
+    _assert_same(o, r1)
