@@ -50,39 +50,54 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, 2 ms period, own thread)."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.rows, self.stop_flag, self.t, self.err = index, [], False, None, None
+        self.max_mhz = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception as e:  # pragma: no cover
+            self.err = f"nvml unavailable: {e}"
+            return
+        self.t = threading.Thread(target=self._run, daemon=True)
+        self.t.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+    def _run(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((float(mhz), int(rs)))
+            except Exception as e:  # pragma: no cover
+                self.err = str(e)
+                return
+            time.sleep(0.002)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
-        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].startswith("Active")})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        if self.t is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.err or "not started"]}
+        self.stop_flag = True
+        self.t.join(timeout=1.0)
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        sm = sorted(r[0] for r in self.rows)
+        reasons = sorted({k for k, bit in names.items() for r in self.rows if r[1] & bit})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                "samples": len(sm)}
 
 
 def make_inputs(torch, B, gamma, V, dtype, sigma, seed, device, nbuf):
@@ -127,12 +142,24 @@ def run_ours(args):
         toks.append(tk.reshape(B, g))
     seq0 = rank * B
 
+    pending = []
+
     def step(i, ev=None):
         t, d = sets[i % nbuf]
         r = sd.fused_verify(t, d, toks[i % nbuf], None, None, seed=2025, offset=i, seq_id0=seq0, **mode)
         if world > 1:
-            return sd.dist.all_gather_packed(r.packed, world * B)
+            # the gathered result is global bookkeeping; a rank continues on its own sequences, so the
+            # 768-byte all-gather runs on NCCL's stream and overlaps the next verify step
+            out, work = sd.dist.all_gather_packed(r.packed, world * B, async_op=True)
+            pending.append(work)
+            if len(pending) > 2:
+                pending.pop(0).wait()
+            return out
         return r.packed
+
+    def drain():
+        while pending:
+            pending.pop(0).wait()
 
     def sync_all():
         if world > 1:
@@ -141,6 +168,7 @@ def run_ours(args):
 
     for i in range(args.warmup):
         step(i)
+    drain()
     sync_all()
 
     # ---- timed region: K steps, device-resident inputs; per-kernel events through the C-ABI hook
@@ -159,6 +187,7 @@ def run_ours(args):
         lib.specdec_set_profile_events(evs[i][0].cuda_event, evs[i][1].cuda_event, evs[i][2].cuda_event)
         step(args.warmup + i)
     lib.specdec_set_profile_events(None, None, None)
+    drain()
     e1.record()
     sync_all()
     ms_total = e0.elapsed_time(e1)
@@ -207,9 +236,36 @@ def run_ours(args):
     h2d = ht.numel() * ht.element_size() + hd.numel() * hd.element_size() + htok.numel() * 8
     d2h = hout.numel() * 4
 
+    # ---- secondary sweep (not the headline): other processor modes on the same inputs, few steps each
+    sweep = {}
+    if world == 1 and not args.no_sweep:
+        for mname in ("greedy", "topk50", "topk50_p0.9", "nucleus0.9"):
+            md = MODES[mname]
+            tk = [sd.sample_rows(d.reshape(B * g, V), None, seed=4321, offset=0, seq_id0=0, **md)[0].reshape(B, g)
+                  for (t, d) in sets]
+            for i in range(3):
+                sd.fused_verify(sets[i % nbuf][0], sets[i % nbuf][1], tk[i % nbuf], None, None, seed=1, offset=i, **md)
+            torch.cuda.synchronize()
+            ks = 5 if mname == "nucleus0.9" else 20
+            e0.record()
+            for i in range(ks):
+                sd.fused_verify(sets[i % nbuf][0], sets[i % nbuf][1], tk[i % nbuf], None, None, seed=1, offset=i, **md)
+            e1.record()
+            torch.cuda.synchronize()
+            msm = e0.elapsed_time(e1) / ks
+            sweep[mname] = {"tokens_per_s": B * g / (msm * 1e-3), "ms_per_step": msm,
+                            "step_frac_of_hbm_peak": alg_bytes(B, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.exists(tp) and dtype == "bf16" and (B, g, V) == (256, 4, 128256):
+            try:
+                traffic = float(json.load(open(tp))["rowfast_tma_kernel_dram_bytes_per_launch"])
+            except Exception:
+                traffic = None
         ab = alg_bytes(B, g, V, dtype)
         ach = ab / (t_rowstats * 1e-3) / 1e9
         out = {
@@ -220,17 +276,20 @@ def run_ours(args):
                                    f"sigma={args.sigma} (BASELINE.json configs[1])",
                        "l2": f"inputs {ab / 1e6:.0f} MB per step > 126 MB L2, rotated over {nbuf} buffers",
                        "parallelism": f"dp{world} (sequences sharded by rank, all-gather of packed results)"},
-            "roofline": {"bound": "hbm", "kernel": "rowstats_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+            "roofline": {"bound": "hbm", "kernel": "rowfast_tma_kernel" if dtype != "f32" else "rowfast_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
+                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "kernel_ms": t_rowstats, "decide_kernel_ms": t_decide,
                          "step_frac": ab / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / Ke},
-            "gpu_launches": 2 * (K + Ke + 2),
+            "gpu_launches": 4 * (K + Ke + 2 + args.warmup),  # row stats, plan, exact rows, sample per verify call
             "clocks": clocks,
         }
+        if sweep:
+            out["sweep"] = sweep
     if world > 1:
         dist.barrier()
+        dist.destroy_process_group()
     return out
 
 
@@ -267,7 +326,7 @@ def cpu_reference_leg(args, steps, warmup, all_threads=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="multinomial", choices=list(MODES))
@@ -280,6 +339,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-sample-B", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))

@@ -221,36 +221,62 @@ __device__ void select_cut(const Src& src, int V, int top_k, int use_p, u64 tpq,
 // top-k; w = T=1 mass, t0 = thr for the nucleus cut), found bit by bit over the bits in which the
 // candidates actually differ (bf16-origin logits: <= ~12 of 32).
 // ---------------------------------------------------------------------------------------------
-template <bool MASS>
-__device__ __forceinline__ unsigned warp_select_key(const float* cz, const u64* cw, int m, unsigned common, unsigned vary,
-                                                    u64 t0) {
-  const int lane = threadIdx.x & 31;
+// reduction group: warp 0 (BLK = false) or the whole CTA (BLK = true)
+template <bool BLK>
+struct Grp {
+  u64* sh64;
+  unsigned* shu;
+  __device__ __forceinline__ int first() const { return BLK ? threadIdx.x : (threadIdx.x & 31); }
+  __device__ __forceinline__ int stride() const { return BLK ? blockDim.x : 32; }
+  __device__ __forceinline__ u64 sum(u64 v) const { return BLK ? block_sum_u64(v, sh64) : warp_sum_u64(v); }
+  __device__ __forceinline__ unsigned orr(unsigned v) const {
+    v = __reduce_or_sync(0xffffffffu, v);
+    if (!BLK) return v;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    if (lane == 0) shu[w] = v;
+    __syncthreads();
+    unsigned t = (lane < nw) ? shu[lane] : 0u;
+    t = __reduce_or_sync(0xffffffffu, t);
+    __syncthreads();
+    return t;
+  }
+  __device__ __forceinline__ void sync() const { if (BLK) __syncthreads(); else __syncwarp(); }
+};
+
+// largest key K with sum_{key_i >= K} w_i > t0, searched over the bits in which the keys differ
+template <bool MASS, bool BLK>
+__device__ __forceinline__ unsigned group_select_key(const Grp<BLK>& gp, const float* cz, const u64* cw, int m,
+                                                     unsigned common, unsigned vary, u64 t0) {
   unsigned K = common;
   for (int bit = 31; bit >= 0; --bit) {
     if (!((vary >> bit) & 1u)) continue;
     const unsigned tr = K | (1u << bit);
     u64 loc = 0;
-    for (int i = lane; i < m; i += 32) {
+    for (int i = gp.first(); i < m; i += gp.stride()) {
       if (fkey(cz[i]) >= tr) loc += MASS ? cw[i] : 1ull;
     }
-    loc = warp_sum_u64(loc);
+    loc = gp.sum(loc);
     if (loc > t0) K = tr;
   }
   return K;
 }
 
-__device__ void select_cut_warp(float* cz, int* cj, u64* cw, int n, int V, int top_k, int use_p, u64 tpq, u64 S1_full,
-                                float c, float mc, float c1, float mc1, float& cut_out, int& jcut_out, u64& Sfix_out) {
+// Cut selection among n candidates in shared memory.  Band mode (pure nucleus): the candidates are the
+// elements of one value band; G_off = exact T=1 mass of everything above the band (all kept) and
+// S_above = their tempered weight sum.
+template <bool BLK>
+__device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw, int n, int V, int top_k, int use_p,
+                                 u64 tpq, u64 S1_full, u64 G_off, u64 S_above, float c, float mc, float c1, float mc1,
+                                 float& cut_out, int& jcut_out, u64& Sfix_out) {
   const int lane = threadIdx.x & 31;
   const unsigned k0 = fkey(cz[0]);
   unsigned vary = 0;
-  for (int i = lane; i < n; i += 32) vary |= fkey(cz[i]) ^ k0;
-  vary = __reduce_or_sync(0xffffffffu, vary);
+  for (int i = gp.first(); i < n; i += gp.stride()) vary |= fkey(cz[i]) ^ k0;
+  vary = gp.orr(vary);
   unsigned kthkey = 0;
   int m = n;
-  if (top_k > 0) {
-    kthkey = warp_select_key<false>(cz, cw, n, k0 & ~vary, vary, (u64)top_k - 1ull);
-    // compact the kept candidates to the front
+  if (top_k > 0) {  // (warp group only: top-k candidate sets are small)
+    kthkey = group_select_key<false, BLK>(gp, cz, cw, n, k0 & ~vary, vary, (u64)top_k - 1ull);
     m = 0;
     for (int base = 0; base < n; base += 32) {
       const int i = base + lane;
@@ -270,25 +296,25 @@ __device__ void select_cut_warp(float* cz, int* cj, u64* cw, int n, int V, int t
     u64 loc = 0;
     unsigned v2 = 0;
     const unsigned k1 = fkey(cz[0]);
-    for (int i = lane; i < m; i += 32) {
+    for (int i = gp.first(); i < m; i += gp.stride()) {
       const u64 w = fix40(cweight(cz[i], c1, mc1));
       cw[i] = w;
       loc += w;
       v2 |= fkey(cz[i]) ^ k1;
     }
-    __syncwarp();
-    const u64 Mc = warp_sum_u64(loc);
-    v2 = __reduce_or_sync(0xffffffffu, v2);
+    gp.sync();
+    const u64 Mc = gp.sum(loc);
+    v2 = gp.orr(v2);
     const u64 S1 = (top_k > 0) ? Mc : S1_full;
     const u64 thr = scale_q32(S1, tpq);
-    cutkey = warp_select_key<true>(cz, cw, m, k1 & ~v2, v2, thr);
+    cutkey = group_select_key<true, BLK>(gp, cz, cw, m, k1 & ~v2, v2, thr - G_off);
     u64 g = 0, cnt = 0;
-    for (int i = lane; i < m; i += 32) {
+    for (int i = gp.first(); i < m; i += gp.stride()) {
       const unsigned key = fkey(cz[i]);
       if (key > cutkey) g += cw[i];
       if (key == cutkey) ++cnt;
     }
-    const u64 Gc = warp_sum_u64(g), cntc = warp_sum_u64(cnt);
+    const u64 Gc = G_off + gp.sum(g), cntc = gp.sum(cnt);
     const u64 wc = fix40(cweight(fkey_inv(cutkey), c1, mc1));
     u64 mkeep = cntc;
     if (wc > 0 && thr >= Gc) {
@@ -300,19 +326,19 @@ __device__ void select_cut_warp(float* cz, int* cj, u64* cw, int n, int V, int t
       while (lo < hi) {
         const int mid = (lo + hi) >> 1;
         u64 c2 = 0;
-        for (int i = lane; i < m; i += 32) c2 += (fkey(cz[i]) == cutkey && cj[i] <= mid) ? 1u : 0u;
-        c2 = warp_sum_u64(c2);
+        for (int i = gp.first(); i < m; i += gp.stride()) c2 += (fkey(cz[i]) == cutkey && cj[i] <= mid) ? 1u : 0u;
+        c2 = gp.sum(c2);
         if (c2 >= mkeep) hi = mid; else lo = mid + 1;
       }
       jcut = lo;
     }
   }
   u64 loc = 0;
-  for (int i = lane; i < m; i += 32) {
+  for (int i = gp.first(); i < m; i += gp.stride()) {
     const unsigned key = fkey(cz[i]);
     if (key > cutkey || (key == cutkey && cj[i] <= jcut)) loc += fix40(cweight(cz[i], c, mc));
   }
-  Sfix_out = warp_sum_u64(loc);
+  Sfix_out = S_above + gp.sum(loc);
   cut_out = fkey_inv(cutkey);
   jcut_out = jcut;
 }
@@ -320,8 +346,12 @@ __device__ void select_cut_warp(float* cz, int* cj, u64* cw, int n, int V, int t
 // ---------------------------------------------------------------------------------------------
 // rowstats_kernel
 // ---------------------------------------------------------------------------------------------
-template <int DT>
-__global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
+template <int DT, bool HK, bool HP>
+__global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
+  // specialised per mask type so that each instantiation only carries its own code path
+  RowJob job = job_in;
+  if (!HK) job.top_k = 0;
+  if (!HP) job.use_p = 0;
   extern __shared__ __align__(16) unsigned char dyn_smem[];
   __shared__ u64 sh64[33];
   __shared__ float shf[33];
@@ -332,7 +362,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
   __shared__ u64 s_Sfix;
   const int V = job.V;
   const float c = job.c;
-  const bool masked = (job.top_k > 0) || job.use_p;
+  constexpr bool masked = HK || HP;
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
     const void* row = row_ptr<DT>(job, r);
     const bool aligned = (((size_t)row) & 15) == 0;
@@ -370,7 +400,9 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
       tau[3] = block_min_f(tmax, shf);
       int L = -1;
       u64 S1 = 0;
-      if (job.top_k > 0) {
+      float band_lo = -INFINITY, band_hi = INFINITY;  // pure-nucleus band; otherwise [tau[L], +inf)
+      u64 band_G = 0;
+      if (HK) {
         if (job.top_k <= RS_NT) {
           // threshold = k-th largest of the per-thread maxima: >= k elements are guaranteed above it and
           // only ~k(1+k/2T) are expected.  Bit-wise bisection, one hardware barrier-count per varying bit.
@@ -395,43 +427,80 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
           L = -1;
         }
       } else {
-        // pure nucleus: exact T=1 mass of the row and of the four nested candidate sets
-        u64 sa = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-        unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-        const float t0 = tau[0], t1 = tau[1], t2 = tau[2], t3 = tau[3];
-        sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
+        // pure nucleus: narrow the value band [band_lo, band_hi) that contains the cut using EXACT
+        // cumulative masses: every sweep accumulates the T=1 mass / count above four nested
+        // thresholds (exp only for elements inside the current range), until the band fits CAP.
+        float hi = INFINITY;   // elements >= hi are known to be kept; G_hi = their exact mass
+        u64 G_hi = 0, thr = 0;
+        float t0 = tau[0], t1 = tau[1], t2 = tau[2], t3 = tau[3];
+        bool first = true;
+        for (int iter = 0; iter < 16 && L < 0; ++iter) {
+          u64 sa = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
+          unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
+          sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            const u64 w = fix40(cweight(x[k], c1, mc1));
-            sa += w;
-            if (x[k] >= t3 && j0 + k < V) {
-              m3 += w; ++n3;
-              if (x[k] >= t2) {
-                m2 += w; ++n2;
-                if (x[k] >= t1) {
-                  m1 += w; ++n1;
-                  if (x[k] >= t0) { m0 += w; ++n0; }
+            for (int k = 0; k < 8; ++k) {
+              const float z = x[k];
+              const bool in = (z >= t3) && (z < hi) && (j0 + k < V);
+              if (first || in) {
+                const u64 w = fix40(cweight(z, c1, mc1));
+                if (first) sa += w;
+                if (in) {
+                  m3 += w; ++n3;
+                  if (z >= t2) {
+                    m2 += w; ++n2;
+                    if (z >= t1) {
+                      m1 += w; ++n1;
+                      if (z >= t0) { m0 += w; ++n0; }
+                    }
+                  }
                 }
               }
             }
-          }
-        });
-        S1 = block_sum_u64(sa, sh64);
-        const u64 M[4] = {block_sum_u64(m0, sh64), block_sum_u64(m1, sh64), block_sum_u64(m2, sh64),
-                          block_sum_u64(m3, sh64)};
-        const u64 N[4] = {block_sum_u64(n0, sh64), block_sum_u64(n1, sh64), block_sum_u64(n2, sh64),
-                          block_sum_u64(n3, sh64)};
-        const u64 thr = scale_q32(S1, job.tpq);
+          });
+          if (first) { S1 = block_sum_u64(sa, sh64); thr = scale_q32(S1, job.tpq); first = false; }
+          const u64 M[4] = {block_sum_u64(m0, sh64), block_sum_u64(m1, sh64), block_sum_u64(m2, sh64),
+                            block_sum_u64(m3, sh64)};
+          const u64 N[4] = {block_sum_u64(n0, sh64), block_sum_u64(n1, sh64), block_sum_u64(n2, sh64),
+                            block_sum_u64(n3, sh64)};
+          const float T[4] = {t0, t1, t2, t3};
+          int l = -1;
 #pragma unroll
-        for (int l = 3; l >= 0; --l)
-          if (M[l] > thr && N[l] <= (u64)CAP) L = l;
+          for (int q = 3; q >= 0; --q)
+            if (G_hi + M[q] > thr) l = q;
+          if (l >= 0) {  // the cut lies in [T[l], upper)
+            const float lo_v = T[l], up_v = (l == 0) ? hi : T[l - 1];
+            const u64 G_up = G_hi + ((l == 0) ? 0ull : M[l - 1]);
+            const u64 cnt = N[l] - ((l == 0) ? 0ull : N[l - 1]);
+            if (cnt <= (u64)CAP) {
+              band_lo = lo_v; band_hi = up_v; band_G = G_up; L = 0;
+            } else {  // subdivide by value
+              const float top = fminf(up_v, m);
+              const float w4 = (top - lo_v) * 0.25f;
+              if (!(w4 > 0.0f) || !(lo_v + w4 > lo_v) || !(lo_v > -INFINITY)) break;  // cannot split (ties): slow path
+              hi = up_v; G_hi = G_up;
+              t0 = lo_v + 3.0f * w4; t1 = lo_v + 2.0f * w4; t2 = lo_v + w4; t3 = lo_v;
+            }
+          } else {  // the cut is below T[3]: extend downwards
+            if (!(t3 > -INFINITY)) break;
+            float step = fmaxf(t2 - t3, (m - t3) * 0.25f);
+            if (!(step > 0.0f)) step = 1.0f;
+            hi = t3; G_hi += M[3];
+            t0 = hi - step; t1 = hi - 2.0f * step; t2 = hi - 3.0f * step; t3 = hi - 4.0f * step;
+            if (iter >= 8) t3 = -INFINITY;  // give up narrowing: take everything that is left
+          }
+        }
       }
       float* cz = (float*)dyn_smem;
       int* cj = (int*)(dyn_smem + (size_t)CAP * 4);
       u64* cw = (u64*)(dyn_smem + (size_t)CAP * 8);
       int n = 0;
+      u64 S_above = 0;
       if (L >= 0) {
-        const float th = tau[L];
+        const bool band = (job.top_k == 0);
+        const float th = band ? band_lo : tau[L];
+        const float up = band ? band_hi : INFINITY;
+        u64 sab = 0;
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
         {  // warp-aggregated compaction: one shared-memory atomic per warp and element slot; 4 loads in flight
@@ -442,7 +511,8 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
             if (!__any_sync(0xffffffffu, (v < NVr) && (vm >= th))) return;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const bool has = (v < NVr) && (x[k] >= th) && (v * 8 + k < V);
+              if (band && (v < NVr) && (x[k] >= up) && (v * 8 + k < V)) sab += fix40(cweight(x[k], c, mc));
+              const bool has = (v < NVr) && (x[k] >= th) && (x[k] < up) && (v * 8 + k < V);
               const unsigned bal = __ballot_sync(0xffffffffu, has);
               if (bal) {
                 const int leader = __ffs(bal) - 1;
@@ -472,16 +542,23 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job) {
         __syncthreads();
         n = s_count;
         __syncthreads();
-        if (n > CAP || n < job.top_k) L = -1;
+        if (band) S_above = block_sum_u64(sab, sh64);
+        if (n > CAP || n < job.top_k || n == 0) L = -1;
       }
       if (L >= 0 && n <= WARP_SELECT_MAX) {
         if (threadIdx.x < 32) {
-          select_cut_warp(cz, cj, cw, n, V, job.top_k, job.use_p, job.tpq, S1, c, mc, c1, mc1, cut, jcut, Sfix);
+          const Grp<false> gp{sh64, shu};
+          select_cut_group<false>(gp, cz, cj, cw, n, V, job.top_k, job.use_p, job.tpq, S1, band_G, S_above, c, mc, c1, mc1,
+                                  cut, jcut, Sfix);
           if (threadIdx.x == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; }
         }
         __syncthreads();
         cut = s_cut; jcut = s_jcut; Sfix = s_Sfix;
         __syncthreads();
+      } else if (L >= 0 && job.top_k == 0) {
+        const Grp<true> gp{sh64, shu};
+        select_cut_group<true>(gp, cz, cj, cw, n, V, 0, job.use_p, job.tpq, S1, band_G, S_above, c, mc, c1, mc1, cut, jcut,
+                               Sfix);
       } else if (L >= 0) {
         CandSrc src{cz, cj, cw, n, c1, mc1};
         select_cut(src, V, job.top_k, job.use_p, job.tpq, S1, c, mc, sh64, shu, cut, jcut, Sfix);
@@ -969,13 +1046,22 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   if (rj.R == 0) return cudaSuccess;
   const bool masked = rj.top_k > 0 || rj.use_p;
   const size_t smem = masked ? CAND_SMEM : 0;
-  if (masked) {
-    cudaError_t e = cudaFuncSetAttribute(rowstats_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-  }
   const long long cap = 2LL * num_sms();
   const int grid = (int)(rj.R < cap ? rj.R : cap);
-  rowstats_kernel<DT><<<grid, RS_NT, smem, st>>>(rj);
+#define RS_LAUNCH(HKv, HPv)                                                                                         \
+  do {                                                                                                              \
+    if (masked) {                                                                                                   \
+      cudaError_t e = cudaFuncSetAttribute(rowstats_kernel<DT, HKv, HPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           (int)smem);                                                              \
+      if (e != cudaSuccess) return e;                                                                               \
+    }                                                                                                               \
+    rowstats_kernel<DT, HKv, HPv><<<grid, RS_NT, smem, st>>>(rj);                                                    \
+  } while (0)
+  if (rj.top_k > 0 && rj.use_p) RS_LAUNCH(true, true);
+  else if (rj.top_k > 0) RS_LAUNCH(true, false);
+  else if (rj.use_p) RS_LAUNCH(false, true);
+  else RS_LAUNCH(false, false);
+#undef RS_LAUNCH
   return cudaGetLastError();
 }
 

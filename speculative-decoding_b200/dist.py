@@ -31,17 +31,20 @@ def pack_results(n_accepted: torch.Tensor, draft_tokens: torch.Tensor, next_toke
     return out
 
 
-def all_gather_packed(packed_local: torch.Tensor, total: int, group=None) -> torch.Tensor:
-    """All-gather the packed per-sequence results of every rank -> [total, gamma+2] (global order)."""
+def all_gather_packed(packed_local: torch.Tensor, total: int, group=None, async_op: bool = False):
+    """All-gather the packed per-sequence results of every rank -> [total, gamma+2] (global order).
+    async_op=True (even shards only) returns (out, work): the collective runs on NCCL's own stream so the
+    next verify step overlaps it; call work.wait() before reading `out`."""
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return packed_local
+        return (packed_local, None) if async_op else packed_local
     world = dist.get_world_size(group)
     width = packed_local.shape[1]
     base, rem = divmod(total, world)
     if rem == 0:  # even shards: one all_gather_into_tensor (single NCCL all-gather)
         out = torch.empty((total, width), dtype=packed_local.dtype, device=packed_local.device)
-        dist.all_gather_into_tensor(out, packed_local.contiguous(), group=group)
-        return out
+        work = dist.all_gather_into_tensor(out, packed_local.contiguous(), group=group, async_op=async_op)
+        return (out, work) if async_op else out
+    assert not async_op, "async all-gather needs evenly divisible shards"
     mx = base + 1
     pad = torch.full((mx, width), -1, dtype=packed_local.dtype, device=packed_local.device)
     pad[:packed_local.shape[0]] = packed_local
