@@ -256,6 +256,44 @@ def run_ours(args):
             sweep[mname] = {"tokens_per_s": B * g / (msm * 1e-3), "ms_per_step": msm,
                             "step_frac_of_hbm_peak": alg_bytes(B, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
 
+        # LLM-like (peaked) rows: a few dominant tokens, so the nucleus is small (the flat 3*randn rows above are
+        # the worst case for top-p: ~5 % of the vocabulary is kept)
+        gpk = torch.Generator(device=dev).manual_seed(99)
+        tp_ = sets[0][0].float() * 0.5
+        idx = torch.randint(V, (B, g + 1, 24), device=dev, generator=gpk)
+        tp_.scatter_(2, idx, 12.0 + 8.0 * torch.rand(B, g + 1, 24, device=dev, generator=gpk))
+        dp_ = (tp_[:, :g] + 0.3 * torch.randn(B, g, V, device=dev, generator=gpk)).to(sets[0][0].dtype)
+        tp_ = tp_.to(sets[0][0].dtype)
+        for mname in ("nucleus0.9", "topk50_p0.9"):
+            md = MODES[mname]
+            tk = sd.sample_rows(dp_.reshape(B * g, V), None, seed=4321, offset=0, seq_id0=0, **md)[0].reshape(B, g)
+            for i in range(3):
+                sd.fused_verify(tp_, dp_, tk, None, None, seed=1, offset=i, **md)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(10):
+                sd.fused_verify(tp_, dp_, tk, None, None, seed=1, offset=i, **md)
+            e1.record()
+            torch.cuda.synchronize()
+            msm = e0.elapsed_time(e1) / 10
+            sweep[mname + "_peaked_rows"] = {"tokens_per_s": B * g / (msm * 1e-3), "ms_per_step": msm,
+                                             "step_frac_of_hbm_peak": alg_bytes(B, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
+        del tp_, dp_
+        # latency at small batch (headline mode)
+        for Bs in (1, 8, 32, 64):
+            t, d = sets[0]
+            for i in range(3):
+                sd.fused_verify(t[:Bs], d[:Bs], toks[0][:Bs], None, None, seed=1, offset=i, **mode)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(20):
+                sd.fused_verify(t[:Bs], d[:Bs], toks[0][:Bs], None, None, seed=1, offset=i, **mode)
+            e1.record()
+            torch.cuda.synchronize()
+            msm = e0.elapsed_time(e1) / 20
+            sweep[f"{args.mode}_B{Bs}"] = {"tokens_per_s": Bs * g / (msm * 1e-3), "ms_per_step": msm,
+                                           "step_frac_of_hbm_peak": alg_bytes(Bs, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
+
     out = None
     if rank == 0:
         peak, peak_src = peaks()

@@ -97,7 +97,9 @@ SPECDEC_API int specdec_verify(const void* target_logits, const void* draft_logi
 /* Measurement hook (bench.py): when non-NULL, specdec_verify records these cudaEvent_t on its stream
  * before the row-statistics kernel, between the two kernels and after the decide kernel. */
 SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end);
-/* Test hook: "force_ldg"=1 makes the row kernel use vectorised LDG instead of the TMA pipeline. */
+/* Test hooks: "force_ldg"=1 makes the row kernel use vectorised LDG instead of the TMA pipeline;
+ * "no_overlap"=0 enables an optional two-stream half-batch pipelining of the verify step (default 1 = off:
+ * measured no gain on B200, the step is instruction-issue bound). */
 SPECDEC_API int specdec_set_option(const char* name, int value);
 
 /* LogitsProcessor.__call__ materialised: probs[rows,V] fp32 = softmax(_process(logits)/T)

@@ -39,8 +39,22 @@ __device__ __forceinline__ float cexp2(float t) {
   p = __fmaf_rn(p, f, 1.0f);
   return __int_as_float(__float_as_int(p) + (int)((unsigned)i << 23));
 }
-// weight of logit z under (c, mc): exp2(z*c - m*c), one rounding in the exponent argument
-__device__ __forceinline__ float cweight(float z, float c, float mc) { return cexp2(__fmaf_rn(z, c, -mc)); }
+// cexp2 for arguments known to be <= 126 (every weight: z <= row max => t <= ~0).  Bit-identical to
+// cexp2 there; saves the upper clamp and the integer subtraction (0x4B400000 << 23 == 0 mod 2^32).
+__device__ __forceinline__ float cexp2_le(float t) {
+  t = fmaxf(t, -125.0f);
+  const float r = __fadd_rn(t, 12582912.0f);
+  const float f = __fsub_rn(t, __fsub_rn(r, 12582912.0f));
+  float p = SPECDEC_C5;
+  p = __fmaf_rn(p, f, SPECDEC_C4);
+  p = __fmaf_rn(p, f, SPECDEC_C3);
+  p = __fmaf_rn(p, f, SPECDEC_C2);
+  p = __fmaf_rn(p, f, SPECDEC_C1);
+  p = __fmaf_rn(p, f, 1.0f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+// weight of logit z (<= row max m) under (c, mc): exp2(z*c - m*c), one rounding in the exponent argument
+__device__ __forceinline__ float cweight(float z, float c, float mc) { return cexp2_le(__fmaf_rn(z, c, -mc)); }
 __device__ __forceinline__ u64 fix40(float x) { return __float2ull_rz(__fmul_rn(x, 1099511627776.0f)); }
 __device__ __forceinline__ u64 fix60(float x) { return __float2ull_rz(__fmul_rn(x, 1152921504606846976.0f)); }
 __device__ __forceinline__ unsigned u24_of(float u) {
@@ -66,6 +80,13 @@ __device__ __forceinline__ unsigned fkey(float z) {
 __device__ __forceinline__ float fkey_inv(unsigned k) {
   unsigned b = (k & 0x80000000u) ? (k ^ 0x80000000u) : ~k;
   return __uint_as_float(b);
+}
+
+// MUFU ex2 (SASS MUFU.EX2): used only where ~1e-6 relative accuracy suffices
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
 // ---- Philox4x32-10, keyed by (seed; offset, global sequence id, lane) ----

@@ -43,11 +43,6 @@ struct HybridWs {
   int nseg_pad;
 };
 
-__device__ __forceinline__ float ex2_approx(float x) {
-  float y;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-  return y;
-}
 
 __device__ __forceinline__ float job_u_accept(const DecideJob& job, int b, int i) {
   return job.u_accept ? job.u_accept[(long long)b * job.gamma + i]
@@ -412,6 +407,65 @@ __device__ void finalize_sequence(const DecideJob& job, const HybridWs& ws, int 
   }
 }
 
+// per-256-element integer partial sums of the sampling weights of segments [s0, s1) (one warp per
+// segment, two segments in flight).  RESID: weights fix60(max(0, P - Q)); else fix40(e) of the target row.
+// Elements past V read as -inf => weight exactly 0, so only the greedy arg-max needs a bounds check.
+template <int DT, bool MASKED, bool GREEDY, bool RESID>
+__device__ __forceinline__ void partial_loop(const void* prowp, const void* qrowp, const RowOut& rp, const RowOut& rq,
+                                             bool pal, bool qal, int V, float c, int s0, int s1, u64* part, u64& tot,
+                                             float& best, int& bidx) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int NV = (V + 7) >> 3;
+  const float mcp = rp.mc, mcq = rq.mc, invp = rp.inv, invq = rq.inv;
+  auto seg_sum = [&](const float(&xp)[8], const float(&xq)[8], int v) -> u64 {
+    u64 s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int j = v * 8 + k;
+      float val;
+      if (RESID) {
+        const bool kp = !MASKED || kept(rp, xp[k], j), kq = !MASKED || kept(rq, xq[k], j);
+        const float P = __fmul_rn(kp ? cweight(xp[k], c, mcp) : 0.0f, invp);
+        const float Q = __fmul_rn(kq ? cweight(xq[k], c, mcq) : 0.0f, invq);
+        val = fmaxf(__fsub_rn(P, Q), 0.0f);
+        s += fix60(val);
+      } else {
+        const bool kp = !MASKED || kept(rp, xp[k], j);
+        val = kp ? cweight(xp[k], c, mcp) : 0.0f;
+        s += fix40(val);
+      }
+      if (GREEDY && j < V && val > best) { best = val; bidx = j; }
+    }
+    return s;
+  };
+  constexpr int WPB = PT / 32;
+  int seg = s0 + w;
+  for (; seg + WPB < s1; seg += 2 * WPB) {
+    const int va = seg * 32 + lane, vb = (seg + WPB) * 32 + lane;
+    float xpa[8], xqa[8], xpb[8], xqb[8];
+    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
+    load8<DT>(prowp, min(vb, NV - 1), V, pal, xpb);
+    if (RESID) {
+      load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
+      load8<DT>(qrowp, min(vb, NV - 1), V, qal, xqb);
+    }
+    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
+    u64 sb = (vb < NV) ? seg_sum(xpb, xqb, vb) : 0ull;
+    sa = warp_sum_u64(sa);
+    sb = warp_sum_u64(sb);
+    if (lane == 0) { part[seg] = sa; part[seg + WPB] = sb; tot += sa + sb; }
+  }
+  for (; seg < s1; seg += WPB) {
+    const int va = seg * 32 + lane;
+    float xpa[8], xqa[8];
+    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
+    if (RESID) load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
+    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
+    sa = warp_sum_u64(sa);
+    if (lane == 0) { part[seg] = sa; tot += sa; }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // grid (B, CH): integer partial sums of the sampling weights; tail = finalize
 // ---------------------------------------------------------------------------------------------
@@ -440,7 +494,6 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
     rq = resolved_row(rj, ws, r2);
     qal = (((size_t)qrowp) & 15) == 0;
   }
-  const float c = rj.c;
   const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
   const int per = (nseg + CH - 1) / CH;
   const int s0 = ch * per, s1 = min(nseg, s0 + per);
@@ -448,56 +501,10 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
   float best = (mode == 2) ? 0.0f : -1.0f;
   int bidx = 0x7FFFFFFF;
   u64* part = ws.part + (size_t)b * ws.nseg_pad;
-  auto seg_sum = [&](const float(&xp)[8], const float(&xq)[8], int v) -> u64 {
-    u64 s = 0;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int j = v * 8 + k;
-      float val;
-      u64 wk;
-      if (mode == 2) {
-        const bool kp = !MASKED || kept(rp, xp[k], j), kq = !MASKED || kept(rq, xq[k], j);
-        const float P = __fmul_rn(kp ? cweight(xp[k], c, rp.mc) : 0.0f, rp.inv);
-        const float Q = __fmul_rn(kq ? cweight(xq[k], c, rq.mc) : 0.0f, rq.inv);
-        val = __fsub_rn(P, Q);
-        val = (val > 0.0f && j < V) ? val : 0.0f;
-        wk = fix60(val);
-      } else {
-        const bool kp = !MASKED || kept(rp, xp[k], j);
-        val = (kp && j < V) ? cweight(xp[k], c, rp.mc) : 0.0f;
-        wk = fix40(val);
-      }
-      s += wk;
-      if (GREEDY && j < V && val > best) { best = val; bidx = j; }
-    }
-    return s;
-  };
-  constexpr int WPB = PT / 32;
-  int seg = s0 + w;
-  for (; seg + WPB < s1; seg += 2 * WPB) {
-    const int va = seg * 32 + lane, vb = (seg + WPB) * 32 + lane;
-    float xpa[8], xqa[8], xpb[8], xqb[8];
-    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
-    load8<DT>(prowp, min(vb, NV - 1), V, pal, xpb);
-    if (mode == 2) {
-      load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
-      load8<DT>(qrowp, min(vb, NV - 1), V, qal, xqb);
-    }
-    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
-    u64 sb = (vb < NV) ? seg_sum(xpb, xqb, vb) : 0ull;
-    sa = warp_sum_u64(sa);
-    sb = warp_sum_u64(sb);
-    if (lane == 0) { part[seg] = sa; part[seg + WPB] = sb; tot += sa + sb; }
-  }
-  for (; seg < s1; seg += WPB) {
-    const int va = seg * 32 + lane;
-    float xpa[8], xqa[8];
-    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
-    if (mode == 2) load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
-    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
-    sa = warp_sum_u64(sa);
-    if (lane == 0) { part[seg] = sa; tot += sa; }
-  }
+  if (mode == 2)
+    partial_loop<DT, MASKED, GREEDY, true>(prowp, qrowp, rp, rq, pal, qal, V, rj.c, s0, s1, part, tot, best, bidx);
+  else
+    partial_loop<DT, MASKED, GREEDY, false>(prowp, qrowp, rp, rq, pal, qal, V, rj.c, s0, s1, part, tot, best, bidx);
   tot = block_sum_u64(tot, sh64);
   if (GREEDY) {
     // (value, smallest index) max: non-negative floats order like their bit patterns

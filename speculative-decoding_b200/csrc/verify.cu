@@ -42,6 +42,7 @@ struct RowJob {
   u64 tpq;  // floor(top_p * 2^32)
   long long R;
   RowOut* out;
+  int skip_resolved;  // rowstats_kernel: skip rows whose RowOut is already flagged exact
 };
 
 template <int DT>
@@ -267,7 +268,8 @@ __device__ __forceinline__ unsigned group_select_key(const Grp<BLK>& gp, const f
 template <bool BLK>
 __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw, int n, int V, int top_k, int use_p,
                                  u64 tpq, u64 S1_full, u64 G_off, u64 S_above, float c, float mc, float c1, float mc1,
-                                 float& cut_out, int& jcut_out, u64& Sfix_out) {
+                                 float& cut_out, int& jcut_out, u64& Sfix_out, u64 thr_lo = 0, u64 thr_hi = 0,
+                                 int* ambiguous = nullptr) {
   const int lane = threadIdx.x & 31;
   const unsigned k0 = fkey(cz[0]);
   unsigned vary = 0;
@@ -306,7 +308,10 @@ __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw
     const u64 Mc = gp.sum(loc);
     v2 = gp.orr(v2);
     const u64 S1 = (top_k > 0) ? Mc : S1_full;
-    const u64 thr = scale_q32(S1, tpq);
+    // bracket mode: the exact threshold is only known to lie in [thr_lo, thr_hi]; select with thr_hi and
+    // report whether every threshold of the bracket gives the same kept set (selection is monotone in thr)
+    const u64 thr = ambiguous ? thr_hi : scale_q32(S1, tpq);
+    if (ambiguous) *ambiguous = (Mc > thr_hi) ? 0 : 1;
     cutkey = group_select_key<true, BLK>(gp, cz, cw, m, k1 & ~v2, v2, thr - G_off);
     u64 g = 0, cnt = 0;
     for (int i = gp.first(); i < m; i += gp.stride()) {
@@ -320,6 +325,12 @@ __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw
     if (wc > 0 && thr >= Gc) {
       const u64 q = (thr - Gc) / wc + 1ull;
       mkeep = q < cntc ? q : cntc;
+    }
+    if (ambiguous) {
+      u64 mk_lo = cntc;
+      if (Gc > thr_lo) *ambiguous = 1;
+      else if (wc > 0) { const u64 q = (thr_lo - Gc) / wc + 1ull; mk_lo = q < cntc ? q : cntc; }
+      if (mk_lo != mkeep) *ambiguous = 1;
     }
     if (mkeep < cntc) {  // keep the first mkeep ties in ascending index order
       int lo = 0, hi = V - 1;
@@ -364,6 +375,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
   const float c = job.c;
   constexpr bool masked = HK || HP;
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+    if (HP && !HK && job.skip_resolved && (job.out[r].flags & 1)) continue;  // done by nucleus_fast_kernel
     const void* row = row_ptr<DT>(job, r);
     const bool aligned = (((size_t)row) & 15) == 0;
     // sweep 1: row max (+ per-thread maxima, reused as candidate thresholds)
@@ -483,7 +495,12 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
             }
           } else {  // the cut is below T[3]: extend downwards
             if (!(t3 > -INFINITY)) break;
-            float step = fmaxf(t2 - t3, (m - t3) * 0.25f);
+            // band width from the local density: aim at ~CAP/2 elements per band
+            float step = (m - t3) * 0.25f;
+            if (N[3] > N[2] && t2 > t3) {
+              const float dens_step = (t2 - t3) * ((float)(CAP / 2) / (float)(N[3] - N[2]));
+              step = fminf(step, fmaxf(dens_step, (t2 - t3) * 0.25f));
+            }
             if (!(step > 0.0f)) step = 1.0f;
             hi = t3; G_hi += M[3];
             t0 = hi - step; t1 = hi - 2.0f * step; t2 = hi - 3.0f * step; t3 = hi - 4.0f * step;
@@ -500,6 +517,8 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
         const bool band = (job.top_k == 0);
         const float th = band ? band_lo : tau[L];
         const float up = band ? band_hi : INFINITY;
+        // tempered weight of the kept elements above the band: at T == 1 it IS the band search's exact mass
+        const bool band_sum = band && (c != c1);
         u64 sab = 0;
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
@@ -511,7 +530,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
             if (!__any_sync(0xffffffffu, (v < NVr) && (vm >= th))) return;
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              if (band && (v < NVr) && (x[k] >= up) && (v * 8 + k < V)) sab += fix40(cweight(x[k], c, mc));
+              if (band_sum && (v < NVr) && (x[k] >= up) && (v * 8 + k < V)) sab += fix40(cweight(x[k], c, mc));
               const bool has = (v < NVr) && (x[k] >= th) && (x[k] < up) && (v * 8 + k < V);
               const unsigned bal = __ballot_sync(0xffffffffu, has);
               if (bal) {
@@ -542,7 +561,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
         __syncthreads();
         n = s_count;
         __syncthreads();
-        if (band) S_above = block_sum_u64(sab, sh64);
+        if (band) S_above = band_sum ? block_sum_u64(sab, sh64) : band_G;
         if (n > CAP || n < job.top_k || n == 0) L = -1;
       }
       if (L >= 0 && n <= WARP_SELECT_MAX) {
@@ -580,6 +599,124 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
       o.cut = cut; o.jcut = jcut; o.flags = 1; o.Sfix = Sfix;
       job.out[r] = o;
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nucleus_fast_kernel (pure top-p): resolves rows whose nucleus is small -- i.e. real LLM logits --
+// without an exact pass over the vocabulary.  The cut only needs (a) the exact T=1 masses of the few
+// top tokens and (b) thr = top_p * S1, and S1 is only needed to ~1e-4 unless a prefix mass happens to
+// lie that close to thr.  So: sweep 1 = max + online MUFU sum (S1 to 1e-6); sweep 2 = compaction of
+// the candidates above the 64-group threshold + MUFU masses above the nested thresholds; exact masses
+// of the candidates; selection with the bracket [thr(1-1e-4), thr(1+1e-4)].  If both ends of the bracket
+// give the same kept set the result equals the exact one (selection is monotone in thr) and the row is
+// flagged resolved; otherwise rowstats_kernel<.., false, true> redoes it exactly.
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ unsigned shu[33];
+  __shared__ int s_count, s_amb;
+  __shared__ float s_cut;
+  __shared__ int s_jcut;
+  __shared__ u64 s_Sfix;
+  float* cz = (float*)dyn_smem;
+  int* cj = (int*)(dyn_smem + (size_t)CAP * 4);
+  u64* cw = (u64*)(dyn_smem + (size_t)CAP * 8);
+  const int V = job.V, NV = (V + 7) >> 3, lane = threadIdx.x & 31;
+  const float c = job.c, c1 = job.c1;
+  for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+    const void* row = row_ptr<DT>(job, r);
+    const bool aligned = (((size_t)row) & 15) == 0;
+    // sweep 1: exact max, per-thread maxima, online MUFU sum at T = 1
+    float tm = -INFINITY, ts = 0.0f;
+    sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
+      const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+      if (vm > tm) { ts = __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, vm), c1))); tm = vm; }
+      const float mcl = __fmul_rn(tm, c1);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ts = __fadd_rn(ts, ex2_approx(__fmaf_rn(x[k], c1, -mcl)));
+    });
+    const float m = block_max_f(tm, shf);
+    const float mc = __fmul_rn(m, c), mc1 = __fmul_rn(m, c1);
+    ts = (tm > -INFINITY) ? __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, m), c1))) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
+    if (lane == 0) shf[threadIdx.x >> 5] = ts;
+    __syncthreads();
+    float S1f = 0.0f;
+#pragma unroll
+    for (int w = 0; w < RS_NT / 32; ++w) S1f += shf[w];
+    __syncthreads();
+    // candidate threshold: min over the 8-lane-group maxima (>= RS_NT/8 elements above it)
+    float qm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+    qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));
+    qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
+    const float th = block_min_f(qm, shf);
+    // sweep 2: compaction of the candidates (warp-aggregated, vote-gated)
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    for (int base = (threadIdx.x >> 5) << 5; base < NV; base += 4 * RS_NT) {
+      float x[4][8];
+      int vv[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        vv[q] = base + q * RS_NT + lane;
+        load8<DT>(row, min(vv[q], NV - 1), V, aligned, x[q]);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        if (base + q * RS_NT >= NV) break;  // warp-uniform
+        const int v = vv[q];
+        const float vm = fmaxf(fmaxf(fmaxf(x[q][0], x[q][1]), fmaxf(x[q][2], x[q][3])),
+                               fmaxf(fmaxf(x[q][4], x[q][5]), fmaxf(x[q][6], x[q][7])));
+        if (!__any_sync(0xffffffffu, (v < NV) && (vm >= th))) continue;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool has = (v < NV) && (x[q][k] >= th) && (v * 8 + k < V);
+          const unsigned bal = __ballot_sync(0xffffffffu, has);
+          if (bal) {
+            const int leader = __ffs(bal) - 1;
+            int pos = 0;
+            if (lane == leader) pos = atomicAdd(&s_count, __popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, leader);
+            if (has) {
+              const int slot = pos + __popc(bal & ((1u << lane) - 1u));
+              if (slot < CAP) { cz[slot] = x[q][k]; cj[slot] = v * 8 + k; }
+            }
+          }
+        }
+      }
+    }
+    __syncthreads();
+    const int n = s_count;
+    bool ok = (n > 0) && (n <= WARP_SELECT_MAX);
+    if (ok) {
+      if (threadIdx.x < 32) {
+        // S1 in 2^-40 fixed point, bracketed by the MUFU error (1e-4 is ~50x the observed 2e-6)
+        const double S1d = (double)S1f * 1099511627776.0;
+        const u64 thr_lo = scale_q32((u64)(S1d * (1.0 - 1e-4)), job.tpq), thr_hi = scale_q32((u64)(S1d * (1.0 + 1e-4)), job.tpq);
+        const Grp<false> gp{sh64, shu};
+        float cut; int jcut; u64 Sfix; int amb = 1;
+        select_cut_group<false>(gp, cz, cj, cw, n, V, 0, 1, job.tpq, 0ull, 0ull, 0ull, c, mc, c1, mc1, cut, jcut, Sfix,
+                                thr_lo, thr_hi, &amb);
+        if (lane == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; s_amb = amb; }
+      }
+      __syncthreads();
+      ok = (s_amb == 0);
+    }
+    if (threadIdx.x == 0) {
+      RowOut o;
+      o.m = m; o.mc = mc; o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0; o.inv = 0.0f;
+      if (ok) {
+        o.cut = s_cut; o.jcut = s_jcut; o.Sfix = s_Sfix; o.flags = 1;
+        o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(s_Sfix), 0x1p-40f));
+      }
+      job.out[r] = o;
+    }
+    __syncthreads();
   }
 }
 
@@ -1012,6 +1149,7 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 // host side
 // ---------------------------------------------------------------------------------------------
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
+static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_sms = 0;
 static int num_sms() {
@@ -1038,6 +1176,7 @@ static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long t
   rj.tpq = rj.use_p ? (u64)((double)top_p * 4294967296.0) : 0ull;
   rj.R = R;
   rj.out = (RowOut*)workspace;
+  rj.skip_resolved = 0;
   return 0;
 }
 
@@ -1059,7 +1198,22 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   } while (0)
   if (rj.top_k > 0 && rj.use_p) RS_LAUNCH(true, true);
   else if (rj.top_k > 0) RS_LAUNCH(true, false);
-  else if (rj.use_p) RS_LAUNCH(false, true);
+  else if (rj.use_p) {
+    if (!g_no_fast_nucleus) {
+      cudaError_t e = cudaFuncSetAttribute(nucleus_fast_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj);
+      RowJob rj2 = rj;
+      rj2.skip_resolved = 1;
+      {
+        cudaError_t e2 = cudaFuncSetAttribute(rowstats_kernel<DT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e2 != cudaSuccess) return e2;
+        rowstats_kernel<DT, false, true><<<grid, RS_NT, smem, st>>>(rj2);
+      }
+    } else {
+      RS_LAUNCH(false, true);
+    }
+  }
   else RS_LAUNCH(false, false);
 #undef RS_LAUNCH
   return cudaGetLastError();
@@ -1106,6 +1260,89 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   return h;
 }
 
+static int g_no_overlap = 1;  // half-batch pipelining on two streams is OFF by default (measured: no gain, the
+                              // step is issue-bound); specdec_set_option("no_overlap", 0) enables it
+static cudaStream_t g_aux_stream = nullptr;
+static cudaEvent_t g_ev_a1 = nullptr, g_ev_b1 = nullptr;
+
+// phase A: row statistics of the job's rows.  limit_ctas > 0 caps the persistent grid per SM.
+template <int DT>
+static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B, int ctas_per_sm, cudaStream_t st) {
+  const RowJob& rj = dj.rj;
+  const bool masked = rj.top_k > 0 || rj.use_p;
+  cudaError_t e;
+  if (masked) return launch_rowstats<DT>(rj, st);
+  if (dj.gamma == 0) {
+    rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
+    return cudaGetLastError();
+  }
+  const size_t es = (DT == DT_F32) ? 4 : 2;
+  const bool tma_ok = DT != DT_F32 && (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
+                      ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
+                      ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0 && !g_force_ldg;
+  if (tma_ok) {
+    static bool attr_set[3] = {false, false, false};
+    if (!attr_set[DT]) {
+      e = cudaFuncSetAttribute(rowfast_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
+      if (e != cudaSuccess) return e;
+      attr_set[DT] = true;
+    }
+    const long long cap = (long long)ctas_per_sm * num_sms();
+    rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
+  } else {
+    rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
+  }
+  return cudaGetLastError();
+}
+
+// phase B: plan, exact sums of the deciding rows, sampling sweep + finalize
+template <int DT>
+static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws, int B, cudaStream_t st) {
+  const RowJob& rj = dj.rj;
+  const bool masked = rj.top_k > 0 || rj.use_p;
+  plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
+  if (!masked && dj.gamma > 0) exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
+  const dim3 grid((unsigned)B, CH);
+  if (masked) {
+    if (dj.greedy) sample_partial_kernel<DT, true, true><<<grid, PT, 0, st>>>(dj, ws);
+    else sample_partial_kernel<DT, true, false><<<grid, PT, 0, st>>>(dj, ws);
+  } else {
+    if (dj.greedy) sample_partial_kernel<DT, false, true><<<grid, PT, 0, st>>>(dj, ws);
+    else sample_partial_kernel<DT, false, false><<<grid, PT, 0, st>>>(dj, ws);
+  }
+  return cudaGetLastError();
+}
+
+// the sub-job of sequences [b0, b0 + nb)
+template <int DT>
+static void sub_job(const DecideJob& dj, const HybridWs& ws, int b0, int nb, int half, DecideJob& o, HybridWs& w) {
+  o = dj; w = ws;
+  const size_t es = (DT == DT_F32) ? 4 : 2;
+  const int g = dj.gamma, rps = dj.rj.nT + dj.rj.nD;
+  o.rj.tgt = (const char*)dj.rj.tgt + (size_t)b0 * dj.rj.tsb * es;
+  if (dj.rj.drf) o.rj.drf = (const char*)dj.rj.drf + (size_t)b0 * dj.rj.dsb * es;
+  o.rj.R = (long long)nb * rps;
+  o.rj.out = dj.rj.out + (size_t)b0 * rps;
+  if (dj.draft_tokens) o.draft_tokens = dj.draft_tokens + (size_t)b0 * g;
+  if (dj.u_accept) o.u_accept = dj.u_accept + (size_t)b0 * g;
+  if (dj.u_sample) o.u_sample = dj.u_sample + b0;
+  o.seq0 = dj.seq0 + b0;
+  o.n_acc = dj.n_acc + b0; o.next_tok = dj.next_tok + b0; o.first_stop = dj.first_stop + b0;
+  if (dj.mask) o.mask = dj.mask + (size_t)b0 * g;
+  if (dj.p_tok) o.p_tok = dj.p_tok + (size_t)b0 * g;
+  if (dj.q_tok) o.q_tok = dj.q_tok + (size_t)b0 * g;
+  if (dj.next_prob) o.next_prob = dj.next_prob + b0;
+  if (dj.packed) o.packed = dj.packed + (size_t)b0 * (g + 2);
+  w.acc = ws.acc + (size_t)b0 * rps; w.tot = ws.tot + b0; w.best = ws.best + b0;
+  w.ntasks = ws.ntasks + half;
+  w.tasks = ws.tasks + (size_t)b0 * (g > 0 ? g : 1);
+  w.status = ws.status + (size_t)b0 * (g > 0 ? g : 1);
+  w.samp = ws.samp + (size_t)b0 * 4;
+  w.rows_done = ws.rows_done + b0; w.seq_tasks = ws.seq_tasks + b0;
+  w.exact_done = ws.exact_done + b0; w.part_done = ws.part_done + b0;
+  w.part = ws.part + (size_t)b0 * ws.nseg_pad;
+}
+
 template <int DT>
 static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* workspace, int B, cudaStream_t st) {
   const RowJob& rj = dj.rj;
@@ -1113,46 +1350,34 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   HybridWs ws = ws_pointers(wl, workspace, B, rj.R);
   cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st);
   if (e != cudaSuccess) return e;
-  if (g_ev[0]) cudaEventRecord(g_ev[0], st);
-  if (masked || dj.gamma == 0) {
-    if (masked) {
-      e = launch_rowstats<DT>(rj, st);
-      if (e != cudaSuccess) return e;
-    } else {
-      rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
-    }
-    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
-    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);  // statuses (no tasks) + decide
-  } else {
-    const size_t es = (DT == DT_F32) ? 4 : 2;
-    const bool tma_ok = DT != DT_F32 && (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
-                        ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
-                        ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0 && !g_force_ldg;
-    if (tma_ok) {
-      static bool attr_set[3] = {false, false, false};
-      if (!attr_set[DT]) {
-        e = cudaFuncSetAttribute(rowfast_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
-        if (e != cudaSuccess) return e;
-        attr_set[DT] = true;
-      }
-      const long long cap = 3LL * num_sms();
-      rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
-    } else {
-      rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
-    }
-    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
-    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
-    exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
+  // Two half-batches pipelined on two streams: the HBM-bound row kernel of the second half overlaps the
+  // FMA-bound exact/sampling kernels of the first half.  Results do not depend on the split.
+  const bool split = !masked && dj.gamma > 0 && B >= 64 && !g_no_overlap;
+  if (split && !g_aux_stream) {
+    if ((e = cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&g_ev_a1, cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&g_ev_b1, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
-  {
-    const dim3 grid((unsigned)B, CH);
-    if (masked) {
-      if (dj.greedy) sample_partial_kernel<DT, true, true><<<grid, PT, 0, st>>>(dj, ws);
-      else sample_partial_kernel<DT, true, false><<<grid, PT, 0, st>>>(dj, ws);
-    } else {
-      if (dj.greedy) sample_partial_kernel<DT, false, true><<<grid, PT, 0, st>>>(dj, ws);
-      else sample_partial_kernel<DT, false, false><<<grid, PT, 0, st>>>(dj, ws);
-    }
+  if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+  if (!split) {
+    if ((e = launch_phase_a<DT>(dj, ws, B, 3, st)) != cudaSuccess) return e;
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    if ((e = launch_phase_b<DT>(dj, ws, B, st)) != cudaSuccess) return e;
+  } else {
+    const int B1 = B / 2, B2 = B - B1;
+    DecideJob d1, d2;
+    HybridWs w1, w2;
+    sub_job<DT>(dj, ws, 0, B1, 0, d1, w1);
+    sub_job<DT>(dj, ws, B1, B2, 1, d2, w2);
+    if ((e = launch_phase_a<DT>(d1, w1, B1, 3, st)) != cudaSuccess) return e;
+    cudaEventRecord(g_ev_a1, st);
+    cudaStreamWaitEvent(g_aux_stream, g_ev_a1, 0);
+    if ((e = launch_phase_b<DT>(d1, w1, B1, g_aux_stream)) != cudaSuccess) return e;
+    cudaEventRecord(g_ev_b1, g_aux_stream);
+    if ((e = launch_phase_a<DT>(d2, w2, B2, 2, st)) != cudaSuccess) return e;
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    if ((e = launch_phase_b<DT>(d2, w2, B2, st)) != cudaSuccess) return e;
+    cudaStreamWaitEvent(st, g_ev_b1, 0);
   }
   if (g_ev[2]) cudaEventRecord(g_ev[2], st);
   return cudaGetLastError();
@@ -1248,6 +1473,8 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
 int specdec_set_option(const char* name, int value) {
   if (!name) return SPECDEC_ERR_ARG;
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
+  if (!strcmp(name, "no_overlap")) { g_no_overlap = value; return 0; }
+  if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   return SPECDEC_ERR_ARG;
 }
 

@@ -43,11 +43,23 @@ def _rows_view(logits: Tensor) -> Tuple[Tensor, int, int, int]:
     return x, x.shape[0], V, (x.stride(0) if x.shape[0] > 1 else V)
 
 
-@torch.library.custom_op("specdec::verify", mutates_args=())
-def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_tokens: Tensor,
-              u_accept: Optional[Tensor], u_sample: Optional[Tensor], seed: int, offset: int, seq_id0: int,
-              temperature: float, top_k: int, top_p: float, sample_mode: int, flags: int,
-              stop_tokens: Optional[Tensor]) -> List[Tensor]:
+_WS_CACHE = {}
+
+
+def _workspace(dev, nbytes: int) -> Tensor:
+    """Per-device scratch, grown on demand and reused across calls (all use is stream-ordered)."""
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _WS_CACHE.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=dev)
+        _WS_CACHE[key] = ws
+    return ws
+
+
+def _verify_impl(target_logits: Tensor, draft_logits: Optional[Tensor], draft_tokens: Tensor,
+                 u_accept: Optional[Tensor], u_sample: Optional[Tensor], seed: int, offset: int, seq_id0: int,
+                 temperature: float, top_k: int, top_p: float, sample_mode: int, flags: int,
+                 stop_tokens: Optional[Tensor]) -> List[Tensor]:
     _need_cuda(target_logits, draft_logits, draft_tokens, u_accept, u_sample, stop_tokens)
     if target_logits.dim() != 3:
         raise ValueError("target_logits must be [B, gamma(+1), V]")
@@ -64,37 +76,60 @@ def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_token
             raise ValueError(f"draft_logits must be [B={B}, gamma={gamma}, V={V}], got {tuple(draft_logits.shape)}")
         if draft_logits.stride(-1) != 1:
             draft_logits = draft_logits.contiguous()
-    draft_tokens = draft_tokens.to(device=dev, dtype=torch.int64).reshape(B, gamma).contiguous()
-    if u_accept is not None:
+    if draft_tokens.dtype != torch.int64 or draft_tokens.device != dev or not draft_tokens.is_contiguous() \
+            or draft_tokens.numel() != B * gamma:
+        draft_tokens = draft_tokens.to(device=dev, dtype=torch.int64).reshape(B, gamma).contiguous()
+    if u_accept is not None and (u_accept.dtype != torch.float32 or u_accept.device != dev or not u_accept.is_contiguous()):
         u_accept = u_accept.to(device=dev, dtype=torch.float32).reshape(B, gamma).contiguous()
-    if u_sample is not None:
+    if u_sample is not None and (u_sample.dtype != torch.float32 or u_sample.device != dev or not u_sample.is_contiguous()):
         u_sample = u_sample.to(device=dev, dtype=torch.float32).reshape(B).contiguous()
     n_stop = 0
     if stop_tokens is not None:
-        stop_tokens = stop_tokens.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
+        if stop_tokens.dtype != torch.int64 or stop_tokens.device != dev or not stop_tokens.is_contiguous():
+            stop_tokens = stop_tokens.to(device=dev, dtype=torch.int64).reshape(-1).contiguous()
         n_stop = stop_tokens.numel()
-    n_acc = torch.empty(B, dtype=torch.int32, device=dev)
-    nxt = torch.empty(B, dtype=torch.int64, device=dev)
-    mask = torch.empty((B, gamma), dtype=torch.uint8, device=dev)
-    p_tok = torch.empty((B, gamma), dtype=torch.float32, device=dev)
-    q_tok = torch.empty((B, gamma), dtype=torch.float32, device=dev)
-    fstop = torch.empty(B, dtype=torch.int32, device=dev)
-    nprob = torch.empty(B, dtype=torch.float32, device=dev)
-    packed = torch.empty((B, gamma + 2), dtype=torch.int32, device=dev)
+    # one allocation for all outputs: [n_acc i32 | first_stop i32 | next_prob f32 | p_tok f32 | q_tok f32 |
+    #                                  packed i32 | next_token i64 (8-aligned) | mask u8]
+    g = gamma
+    n32 = 3 * B + 2 * B * g + B * (g + 2)
+    n32 += n32 & 1
+    buf = torch.empty(n32 * 4 + B * 8 + B * g, dtype=torch.uint8, device=dev)
+    i32 = buf[:n32 * 4].view(torch.int32)
+    f32 = buf[:n32 * 4].view(torch.float32)
+    n_acc, fstop, nprob = i32[0:B], i32[B:2 * B], f32[2 * B:3 * B]
+    o = 3 * B
+    p_tok = f32[o:o + B * g].view(B, g); o += B * g
+    q_tok = f32[o:o + B * g].view(B, g); o += B * g
+    packed = i32[o:o + B * (g + 2)].view(B, g + 2)
+    nxt = buf[n32 * 4:n32 * 4 + B * 8].view(torch.int64)
+    mask = buf[n32 * 4 + B * 8:].view(B, g)
     lib = L.lib()
     ws_bytes = lib.specdec_verify_workspace_bytes(B, gamma, V)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, ws_bytes)
     sd = draft_logits.stride() if draft_logits is not None else (0, 0, 1)
-    with torch.cuda.device(dev):
-        rc = lib.specdec_verify(
-            _ptr(target_logits), _ptr(draft_logits), dt, _ptr(draft_tokens), _ptr(u_accept), _ptr(u_sample),
-            seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, seq_id0, B, gamma, V,
-            target_logits.stride(0), target_logits.stride(1), sd[0], sd[1],
-            float(temperature), int(top_k), float(top_p), int(sample_mode), int(flags),
-            _ptr(stop_tokens), n_stop, _ptr(n_acc), _ptr(nxt), _ptr(mask), _ptr(p_tok), _ptr(q_tok), _ptr(fstop),
-            _ptr(nprob), _ptr(packed), _ptr(ws), ws_bytes, _stream())
+    base = buf.data_ptr()
+    if torch.cuda.current_device() != dev.index:
+        torch.cuda.set_device(dev)
+    rc = lib.specdec_verify(
+        target_logits.data_ptr(), _ptr(draft_logits), dt, draft_tokens.data_ptr(), _ptr(u_accept), _ptr(u_sample),
+        seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, seq_id0, B, gamma, V,
+        target_logits.stride(0), target_logits.stride(1), sd[0], sd[1],
+        float(temperature), int(top_k), float(top_p), int(sample_mode), int(flags),
+        _ptr(stop_tokens), n_stop, n_acc.data_ptr(), nxt.data_ptr(), mask.data_ptr() if g else None,
+        p_tok.data_ptr() if g else None, q_tok.data_ptr() if g else None, fstop.data_ptr(),
+        nprob.data_ptr(), packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     L.check(rc, "specdec_verify")
     return [n_acc, nxt, mask, p_tok, q_tok, fstop, nprob, packed]
+
+
+@torch.library.custom_op("specdec::verify", mutates_args=())
+def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_tokens: Tensor,
+              u_accept: Optional[Tensor], u_sample: Optional[Tensor], seed: int, offset: int, seq_id0: int,
+              temperature: float, top_k: int, top_p: float, sample_mode: int, flags: int,
+              stop_tokens: Optional[Tensor]) -> List[Tensor]:
+    # custom ops may not return views of one buffer: clone the (tiny) outputs
+    return [t.clone() for t in _verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, seed, offset,
+                                            seq_id0, temperature, top_k, top_p, sample_mode, flags, stop_tokens)]
 
 
 @verify_op.register_fake
@@ -145,7 +180,8 @@ def sample_rows_op(logits: Tensor, u: Optional[Tensor], seed: int, offset: int, 
     ptok = torch.empty(rows, dtype=torch.float32, device=dev)
     lib = L.lib()
     ws_bytes = lib.specdec_sample_rows_workspace_bytes(rows, V)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    ws = _workspace(dev, ws_bytes)
+    ws_bytes = ws.numel()
     with torch.cuda.device(dev):
         rc = lib.specdec_sample_rows(_ptr(x), _dtype_code(x), rows, V, stride, float(temperature), int(top_k),
                                      float(top_p), int(sample_mode), _ptr(u), seed & 0xFFFFFFFFFFFFFFFF,
@@ -231,9 +267,11 @@ def fused_verify(target_logits, draft_logits, draft_tokens, u_accept=None, u_sam
         stop_tokens = torch.as_tensor(list(stop_tokens), dtype=torch.int64, device=target_logits.device)
     if stop_tokens is not None and stop_tokens.numel() == 0:
         stop_tokens = None
-    return VerifyResult(verify_op(target_logits, draft_logits, draft_tokens, u_accept, u_sample, int(seed), int(offset),
-                                  int(seq_id0), float(temperature), int(top_k), float(top_p),
-                                  L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
+    # direct call of the implementation (same code the registered torch op `specdec::verify` runs) -- skips
+    # the dispatcher's per-call overhead, which matters at small batch
+    return VerifyResult(_verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, int(seed), int(offset),
+                                     int(seq_id0), float(temperature), int(top_k), float(top_p),
+                                     L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
 
 
 def process_probs(logits, temperature=1.0, top_k=0, top_p=1.0):

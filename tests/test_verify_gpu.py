@@ -218,3 +218,61 @@ def test_tma_and_ldg_row_kernels_agree(oracle_mod):
     np.testing.assert_allclose(r1.p_tok.cpu().numpy(), r2.p_tok.cpu().numpy(), rtol=1e-5)
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
     _assert_same(o, r1)
+
+
+def test_half_batch_pipelining_does_not_change_results(oracle_mod):
+    """optional two-stream half-batch pipelining (B >= 64): results equal the single-stream path and the oracle."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    case = make_case(B=70, gamma=3, V=8192, dtype="bf16", sigma=0.6, seed=41, oracle=oracle_mod)
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args, stop_tokens=[5, 77])
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"no_overlap", 0) == 0
+    try:
+        r2 = sd.fused_verify(*args, stop_tokens=[5, 77])
+        torch.cuda.synchronize()
+    finally:
+        lib.specdec_set_option(b"no_overlap", 1)
+    for a, b in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.accept_mask, r2.accept_mask),
+                 (r1.first_stop, r2.first_stop), (r1.packed, r2.packed), (r1.p_tok, r2.p_tok), (r1.next_prob, r2.next_prob)):
+        assert torch.equal(a, b)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"],
+                          stop_tokens=[5, 77])
+    _assert_same(o, r1)
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32"])
+@pytest.mark.parametrize("mode", ["nucleus0.9", "nucleus0.9_t0.7"])
+def test_fast_nucleus_path_on_peaked_rows(oracle_mod, dtype, mode):
+    """LLM-like rows (small nucleus) are resolved by nucleus_fast_kernel (MUFU normaliser + bracketed
+    threshold); results equal the oracle and the exact-only path."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    case = make_case(B=12, gamma=4, V=128256, dtype=dtype, sigma=0.0, seed=17)
+    # LLM-like rows: a handful of tokens carry almost all the mass
+    g = torch.Generator().manual_seed(5)
+    t = case["target"].float() * 0.5
+    idx = torch.randint(128256, (12, 5, 24), generator=g)
+    t.scatter_(2, idx, 12.0 + 8.0 * torch.rand(12, 5, 24, generator=g))
+    d = t[:, :4] + 0.4 * torch.randn(12, 4, 128256, generator=g)
+    case["target"], case["draft"] = t.to(case["target"].dtype), d.to(case["target"].dtype)
+    m = MODES[mode]
+    tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(48, 128256),
+                                    torch.rand(48, generator=g).numpy(), **m)
+    case["draft_tokens"] = torch.from_numpy(tok.reshape(12, 4))
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args, **m)
+    probs_fast, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    assert lib.specdec_set_option(b"no_fast_nucleus", 1) == 0
+    try:
+        r2 = sd.fused_verify(*args, **m)
+        probs_exact, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    finally:
+        lib.specdec_set_option(b"no_fast_nucleus", 0)
+    assert torch.equal(r1.n_accepted, r2.n_accepted) and torch.equal(r1.next_token, r2.next_token)
+    assert torch.equal(r1.p_tok, r2.p_tok) and torch.equal(probs_fast, probs_exact)
+    kept = (probs_fast > 0).sum(-1)
+    assert int(kept.max()) < 1000  # genuinely small nuclei: this case exercises the fast kernel
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
+    _assert_same(o, r1)
