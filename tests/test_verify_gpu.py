@@ -276,3 +276,29 @@ def test_fast_nucleus_path_on_peaked_rows(oracle_mod, dtype, mode):
     assert int(kept.max()) < 1000  # genuinely small nuclei: this case exercises the fast kernel
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
     _assert_same(o, r1)
+
+
+def test_randomised_configurations(oracle_mod):
+    """60 random (B, gamma, V, dtype, processor, flags, sigma) configurations against the oracle."""
+    rng = np.random.RandomState(2024)
+    modes = list(MODES)
+    flag_sets = [0, 0, 0, F_SKIP, F_BATCHED | F_NO_BONUS | F_FALLBACK, F_NO_BONUS, F_BATCHED]
+    for it in range(60):
+        B = int(rng.choice([1, 2, 3, 5, 9, 17, 33, 70]))
+        gamma = int(rng.choice([1, 2, 3, 4, 6, 8]))
+        V = int(rng.choice([8, 100, 1001, 4096, 16384, 32000, 50257]))
+        dtype = str(rng.choice(["f32", "bf16", "f16"]))
+        mode = modes[int(rng.randint(len(modes)))]
+        flags = flag_sets[int(rng.randint(len(flag_sets)))]
+        sigma = float(rng.choice([0.0, 0.3, 1.0, 3.0]))
+        kind = str(rng.choice(["randn", "peaked"]))
+        if B * gamma * V > 6e6:
+            B = max(1, int(6e6 // (gamma * V)))
+        case = make_case(B=B, gamma=gamma, V=V, dtype=dtype, sigma=sigma, seed=1000 + it, kind=kind, oracle=oracle_mod,
+                         mode=mode)
+        stop = [int(case["draft_tokens"][0, 0])] if it % 3 == 0 else []
+        o, r = _run_both(oracle_mod, case, mode, flags=flags, stop=stop)
+        try:
+            _assert_same(o, r)
+        except AssertionError as e:
+            raise AssertionError(f"config {it}: B={B} gamma={gamma} V={V} {dtype} {mode} flags={flags} sigma={sigma} {kind}: {e}")
