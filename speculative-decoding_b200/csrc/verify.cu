@@ -222,6 +222,39 @@ __device__ void select_cut(const Src& src, int V, int top_k, int use_p, u64 tpq,
 // top-k; w = T=1 mass, t0 = thr for the nucleus cut), found bit by bit over the bits in which the
 // candidates actually differ (bf16-origin logits: <= ~12 of 32).
 // ---------------------------------------------------------------------------------------------
+// Warp-cooperative compaction of the elements of one 8-element vector per lane that lie in [th, up):
+// per-lane hit mask -> warp prefix sum -> ONE shared-memory atomic per warp -> predicated stores.
+// (x holds -inf for elements past the row end.)  Must be called by all 32 lanes.
+__device__ __forceinline__ void compact_vec(const float (&x)[8], int v, float th, float up, int V, float* cz, int* cj,
+                                            int* s_count, int cap) {
+  const int lane = threadIdx.x & 31;
+  // hits are usually rare: one vote on the vector maximum skips the per-element work
+  const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+  if (!__any_sync(0xffffffffu, vm >= th)) return;
+  unsigned mask = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if ((x[k] >= th) && (x[k] < up) && (v * 8 + k < V)) mask |= 1u << k;
+  if (!__any_sync(0xffffffffu, mask != 0)) return;
+  const int cnt = __popc(mask);
+  int incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  int base = 0;
+  if (lane == 31) base = atomicAdd(s_count, incl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  int pos = base + incl - cnt;
+#pragma unroll
+  for (int k = 0; k < 8; ++k)
+    if ((mask >> k) & 1u) {
+      if (pos < cap) { cz[pos] = x[k]; cj[pos] = v * 8 + k; }
+      ++pos;
+    }
+}
+
 // reduction group: warp 0 (BLK = false) or the whole CTA (BLK = true)
 template <bool BLK>
 struct Grp {
@@ -438,131 +471,105 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
         } else {
           L = -1;
         }
-      } else {
-        // pure nucleus: narrow the value band [band_lo, band_hi) that contains the cut using EXACT
-        // cumulative masses: every sweep accumulates the T=1 mass / count above four nested
-        // thresholds (exp only for elements inside the current range), until the band fits CAP.
-        float hi = INFINITY;   // elements >= hi are known to be kept; G_hi = their exact mass
-        u64 G_hi = 0, thr = 0;
-        float t0 = tau[0], t1 = tau[1], t2 = tau[2], t3 = tau[3];
-        bool first = true;
-        for (int iter = 0; iter < 16 && L < 0; ++iter) {
-          u64 sa = 0, m0 = 0, m1 = 0, m2 = 0, m3 = 0;
-          unsigned n0 = 0, n1 = 0, n2 = 0, n3 = 0;
-          sweep<DT>(row, V, aligned, [&](const float(&x)[8], int j0) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              const float z = x[k];
-              const bool in = (z >= t3) && (z < hi) && (j0 + k < V);
-              if (first || in) {
-                const u64 w = fix40(cweight(z, c1, mc1));
-                if (first) sa += w;
-                if (in) {
-                  m3 += w; ++n3;
-                  if (z >= t2) {
-                    m2 += w; ++n2;
-                    if (z >= t1) {
-                      m1 += w; ++n1;
-                      if (z >= t0) { m0 += w; ++n0; }
-                    }
-                  }
-                }
-              }
-            }
-          });
-          if (first) { S1 = block_sum_u64(sa, sh64); thr = scale_q32(S1, job.tpq); first = false; }
-          const u64 M[4] = {block_sum_u64(m0, sh64), block_sum_u64(m1, sh64), block_sum_u64(m2, sh64),
-                            block_sum_u64(m3, sh64)};
-          const u64 N[4] = {block_sum_u64(n0, sh64), block_sum_u64(n1, sh64), block_sum_u64(n2, sh64),
-                            block_sum_u64(n3, sh64)};
-          const float T[4] = {t0, t1, t2, t3};
-          int l = -1;
-#pragma unroll
-          for (int q = 3; q >= 0; --q)
-            if (G_hi + M[q] > thr) l = q;
-          if (l >= 0) {  // the cut lies in [T[l], upper)
-            const float lo_v = T[l], up_v = (l == 0) ? hi : T[l - 1];
-            const u64 G_up = G_hi + ((l == 0) ? 0ull : M[l - 1]);
-            const u64 cnt = N[l] - ((l == 0) ? 0ull : N[l - 1]);
-            if (cnt <= (u64)CAP) {
-              band_lo = lo_v; band_hi = up_v; band_G = G_up; L = 0;
-            } else {  // subdivide by value
-              const float top = fminf(up_v, m);
-              const float w4 = (top - lo_v) * 0.25f;
-              if (!(w4 > 0.0f) || !(lo_v + w4 > lo_v) || !(lo_v > -INFINITY)) break;  // cannot split (ties): slow path
-              hi = up_v; G_hi = G_up;
-              t0 = lo_v + 3.0f * w4; t1 = lo_v + 2.0f * w4; t2 = lo_v + w4; t3 = lo_v;
-            }
-          } else {  // the cut is below T[3]: extend downwards
-            if (!(t3 > -INFINITY)) break;
-            // band width from the local density: aim at ~CAP/2 elements per band
-            float step = (m - t3) * 0.25f;
-            if (N[3] > N[2] && t2 > t3) {
-              const float dens_step = (t2 - t3) * ((float)(CAP / 2) / (float)(N[3] - N[2]));
-              step = fminf(step, fmaxf(dens_step, (t2 - t3) * 0.25f));
-            }
-            if (!(step > 0.0f)) step = 1.0f;
-            hi = t3; G_hi += M[3];
-            t0 = hi - step; t1 = hi - 2.0f * step; t2 = hi - 3.0f * step; t3 = hi - 4.0f * step;
-            if (iter >= 8) t3 = -INFINITY;  // give up narrowing: take everything that is left
-          }
-        }
       }
       float* cz = (float*)dyn_smem;
       int* cj = (int*)(dyn_smem + (size_t)CAP * 4);
       u64* cw = (u64*)(dyn_smem + (size_t)CAP * 8);
-      int n = 0;
-      u64 S_above = 0;
-      if (L >= 0) {
-        const bool band = (job.top_k == 0);
-        const float th = band ? band_lo : tau[L];
-        const float up = band ? band_hi : INFINITY;
-        // tempered weight of the kept elements above the band: at T == 1 it IS the band search's exact mass
-        const bool band_sum = band && (c != c1);
-        u64 sab = 0;
+      // Compaction of the elements in [th, up) into shared memory (warp-aggregated slot allocation, one vote
+      // per vector gates the per-element work, 4 loads in flight).  sa != nullptr additionally accumulates
+      // the exact T=1 mass of EVERY element (pure nucleus, first pass).  Returns the number of elements
+      // in the range (which may exceed CAP: then the buffer content is incomplete).
+      auto collect = [&](const float th, const float up, u64* sa) -> int {
+        const int NVr = (V + 7) >> 3, lane = threadIdx.x & 31;
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
-        {  // warp-aggregated compaction: one shared-memory atomic per warp and element slot; 4 loads in flight
-          const int NVr = (V + 7) >> 3, lane = threadIdx.x & 31;
-          auto emit = [&](const float(&x)[8], int v) {
-            // candidates are rare: one vote per vector decides whether anything has to be emitted
-            const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-            if (!__any_sync(0xffffffffu, (v < NVr) && (vm >= th))) return;
+        auto emit = [&](const float(&x)[8], int v) {
+          if (sa) {
 #pragma unroll
-            for (int k = 0; k < 8; ++k) {
-              if (band_sum && (v < NVr) && (x[k] >= up) && (v * 8 + k < V)) sab += fix40(cweight(x[k], c, mc));
-              const bool has = (v < NVr) && (x[k] >= th) && (x[k] < up) && (v * 8 + k < V);
-              const unsigned bal = __ballot_sync(0xffffffffu, has);
-              if (bal) {
-                const int leader = __ffs(bal) - 1;
-                int pos = 0;
-                if (lane == leader) pos = atomicAdd(&s_count, __popc(bal));
-                pos = __shfl_sync(0xffffffffu, pos, leader);
-                if (has) {
-                  const int slot = pos + __popc(bal & ((1u << lane) - 1u));
-                  if (slot < CAP) { cz[slot] = x[k]; cj[slot] = v * 8 + k; }
-                }
-              }
-            }
-          };
-          for (int base = (threadIdx.x >> 5) << 5; base < NVr; base += 4 * RS_NT) {  // warp-uniform
-            float x0[8], x1[8], x2[8], x3[8];
-            const int v0 = base + lane, v1 = v0 + RS_NT, v2 = v0 + 2 * RS_NT, v3 = v0 + 3 * RS_NT;
-            load8<DT>(row, min(v0, NVr - 1), V, aligned, x0);
-            load8<DT>(row, min(v1, NVr - 1), V, aligned, x1);
-            load8<DT>(row, min(v2, NVr - 1), V, aligned, x2);
-            load8<DT>(row, min(v3, NVr - 1), V, aligned, x3);
-            emit(x0, v0);
-            if (base + RS_NT < NVr) emit(x1, v1);
-            if (base + 2 * RS_NT < NVr) emit(x2, v2);
-            if (base + 3 * RS_NT < NVr) emit(x3, v3);
+            for (int k = 0; k < 8; ++k) *sa += fix40(cweight(x[k], c1, mc1));  // (-inf padding contributes 0)
           }
+          compact_vec(x, v, th, up, V, cz, cj, &s_count, CAP);
+        };
+        for (int base = (threadIdx.x >> 5) << 5; base < NVr; base += 4 * RS_NT) {  // warp-uniform
+          float x0[8], x1[8], x2[8], x3[8];
+          const int v0 = base + lane, v1 = v0 + RS_NT, v2 = v0 + 2 * RS_NT, v3 = v0 + 3 * RS_NT;
+          load8<DT>(row, min(v0, NVr - 1), V, aligned, x0);
+          load8<DT>(row, min(v1, NVr - 1), V, aligned, x1);
+          load8<DT>(row, min(v2, NVr - 1), V, aligned, x2);
+          load8<DT>(row, min(v3, NVr - 1), V, aligned, x3);
+          if (v0 >= NVr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x0[k] = -INFINITY;
+          }
+          if (v1 >= NVr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x1[k] = -INFINITY;
+          }
+          if (v2 >= NVr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x2[k] = -INFINITY;
+          }
+          if (v3 >= NVr) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) x3[k] = -INFINITY;
+          }
+          emit(x0, v0);
+          if (base + RS_NT < NVr) emit(x1, v1);
+          if (base + 2 * RS_NT < NVr) emit(x2, v2);
+          if (base + 3 * RS_NT < NVr) emit(x3, v3);
         }
         __syncthreads();
-        n = s_count;
+        const int cnt = s_count;
         __syncthreads();
-        if (band) S_above = band_sum ? block_sum_u64(sab, sh64) : band_G;
-        if (n > CAP || n < job.top_k || n == 0) L = -1;
+        return cnt;
+      };
+      int n = 0;
+      u64 S_above = 0;
+      if (HK) {
+        if (L >= 0) {
+          n = collect(tau[L], INFINITY, nullptr);
+          if (n > CAP || n < job.top_k || n == 0) L = -1;
+        }
+      } else {
+        // pure nucleus, exact: pass A = exact T=1 mass of the row merged with the compaction of everything
+        // above the thread-maxima threshold; then bands of ~CAP/2 elements are taken downwards (one cheap
+        // compaction sweep each) until the exact cumulative mass crosses thr.  Every consumed band is kept
+        // entirely, so its exact masses are simply added up.
+        u64 sa_local = 0;
+        float lo = tau[3], hi = INFINITY;
+        n = collect(lo, hi, &sa_local);
+        S1 = block_sum_u64(sa_local, sh64);
+        const u64 thr = scale_q32(S1, job.tpq);
+        u64 G_hi = 0;
+        // first band below tau3: ~55 % of the n elements >= tau3 lie in [tau3, tau2) (order statistics of the
+        // thread / pair maxima), which gives the local density; aim at CAP/2 elements with a 0.75 safety factor
+        float width = (m - tau[3]) * 0.125f;
+        if (tau[2] > tau[3] && n > 0) width = (tau[2] - tau[3]) * ((float)(CAP / 2) / (0.55f * (float)n)) * 0.75f;
+        for (int iter = 0; iter < 40; ++iter) {
+          if (n > CAP) {  // too many elements in [lo, hi): halve the band by value
+            const float top = fminf(hi, m);
+            const float mid = lo + (top - lo) * 0.5f;
+            if (!(lo > -INFINITY) || !(mid > lo) || !(mid < top)) break;  // a tie group larger than CAP: slow path
+            lo = mid;
+          } else {
+            u64 loc = 0, locT = 0;
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+              loc += fix40(cweight(cz[i], c1, mc1));
+              if (c != c1) locT += fix40(cweight(cz[i], c, mc));
+            }
+            const u64 Mc = block_sum_u64(loc, sh64);
+            if (G_hi + Mc > thr) { band_G = G_hi; L = 0; break; }  // the cut lies in this band
+            S_above += (c != c1) ? block_sum_u64(locT, sh64) : Mc;
+            G_hi += Mc;
+            if (!(lo > -INFINITY)) break;
+            if (n > 0 && hi < INFINITY) width = (hi - lo) * ((float)(CAP / 2) / (float)n) * 0.75f;  // density grows downwards
+            if (!(width > 0.0f)) width = 1.0f;
+            hi = lo;
+            lo = (iter >= 30) ? -INFINITY : hi - width;
+          }
+          n = collect(lo, hi, nullptr);
+        }
+        if (n == 0 || n > CAP) L = -1;
       }
       if (L >= 0 && n <= WARP_SELECT_MAX) {
         if (threadIdx.x < 32) {
@@ -670,24 +677,11 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
       for (int q = 0; q < 4; ++q) {
         if (base + q * RS_NT >= NV) break;  // warp-uniform
         const int v = vv[q];
-        const float vm = fmaxf(fmaxf(fmaxf(x[q][0], x[q][1]), fmaxf(x[q][2], x[q][3])),
-                               fmaxf(fmaxf(x[q][4], x[q][5]), fmaxf(x[q][6], x[q][7])));
-        if (!__any_sync(0xffffffffu, (v < NV) && (vm >= th))) continue;
+        if (v >= NV) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-          const bool has = (v < NV) && (x[q][k] >= th) && (v * 8 + k < V);
-          const unsigned bal = __ballot_sync(0xffffffffu, has);
-          if (bal) {
-            const int leader = __ffs(bal) - 1;
-            int pos = 0;
-            if (lane == leader) pos = atomicAdd(&s_count, __popc(bal));
-            pos = __shfl_sync(0xffffffffu, pos, leader);
-            if (has) {
-              const int slot = pos + __popc(bal & ((1u << lane) - 1u));
-              if (slot < CAP) { cz[slot] = x[q][k]; cj[slot] = v * 8 + k; }
-            }
-          }
+          for (int k = 0; k < 8; ++k) x[q][k] = -INFINITY;
         }
+        compact_vec(x[q], v, th, INFINITY, V, cz, cj, &s_count, CAP);
       }
     }
     __syncthreads();
