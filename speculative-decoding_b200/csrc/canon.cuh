@@ -151,6 +151,62 @@ __device__ __forceinline__ void load8(const void* row, int v, int V, bool aligne
   }
 }
 
+// Raw (still packed) 8-element vector: lets a thread keep many loads in flight without paying the
+// registers of the unpacked floats.  bf16/f16: 4 registers; f32: 8.
+template <int DT> struct Raw8 { uint4 a; };
+template <> struct Raw8<DT_F32> { uint4 a, b; };
+
+template <int DT>
+__device__ __forceinline__ Raw8<DT> load_raw8(const void* row, int v, int V, bool aligned) {
+  Raw8<DT> r;
+  const int j0 = v * 8;
+  if (aligned && j0 + 8 <= V) {
+    if constexpr (DT == DT_F32) {
+      const uint4* p = (const uint4*)((const float*)row + j0);
+      r.a = __ldg(p); r.b = __ldg(p + 1);
+    } else {
+      r.a = __ldg((const uint4*)((const unsigned short*)row + j0));
+    }
+  } else {  // ragged tail / unaligned row: scalar loads, -inf padding
+    if constexpr (DT == DT_F32) {
+      unsigned w[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) w[k] = (j0 + k < V) ? __float_as_uint(__ldg((const float*)row + j0 + k)) : 0xFF800000u;
+      r.a = make_uint4(w[0], w[1], w[2], w[3]); r.b = make_uint4(w[4], w[5], w[6], w[7]);
+    } else {
+      const unsigned ninf = (DT == DT_BF16) ? 0xFF80u : 0xFC00u;
+      unsigned w[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const unsigned lo = (j0 + 2 * k < V) ? (unsigned)__ldg((const unsigned short*)row + j0 + 2 * k) : ninf;
+        const unsigned hi = (j0 + 2 * k + 1 < V) ? (unsigned)__ldg((const unsigned short*)row + j0 + 2 * k + 1) : ninf;
+        w[k] = lo | (hi << 16);
+      }
+      r.a = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+  return r;
+}
+template <int DT>
+__device__ __forceinline__ void unpack8(const Raw8<DT>& r, float (&x)[8]) {
+  if constexpr (DT == DT_F32) {
+    x[0] = __uint_as_float(r.a.x); x[1] = __uint_as_float(r.a.y); x[2] = __uint_as_float(r.a.z); x[3] = __uint_as_float(r.a.w);
+    x[4] = __uint_as_float(r.b.x); x[5] = __uint_as_float(r.b.y); x[6] = __uint_as_float(r.b.z); x[7] = __uint_as_float(r.b.w);
+  } else {
+    const unsigned w[4] = {r.a.x, r.a.y, r.a.z, r.a.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if constexpr (DT == DT_BF16) {
+        x[2 * k] = __uint_as_float(w[k] << 16);
+        x[2 * k + 1] = __uint_as_float(w[k] & 0xFFFF0000u);
+      } else {
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+        x[2 * k] = f.x; x[2 * k + 1] = f.y;
+      }
+    }
+  }
+}
+
 // ---- block-wide reductions for NT = 1024 threads (32 warps); `sh` = 33-entry scratch ----
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll

@@ -259,33 +259,55 @@ __global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs w
 #include "rowfast_tma.cuh"
 
 // ---------------------------------------------------------------------------------------------
-// canonical sums of the task rows: grid (B*gamma, CH); tail = decide
+// canonical sums of the task rows: grid (B, CH), tasks looped over; tail = decide
 // ---------------------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, HybridWs ws) {
   __shared__ u64 sh64[33];
   __shared__ int sh_last;
-  if ((int)blockIdx.x >= *ws.ntasks) return;
   const RowJob& rj = job.rj;
-  const int task = ws.tasks[blockIdx.x];
+  const int ntasks = *ws.ntasks;
+  for (int tix = blockIdx.x; tix < ntasks; tix += gridDim.x) {  // usually one task per sequence
+  const int task = ws.tasks[tix];
   const int g = job.gamma, rps = rj.nT + rj.nD, V = rj.V;
   const int b = task / g, i = task - b * g;
   const int NV = (V + 7) >> 3, per = (NV + CH - 1) / CH;
   const int v0 = blockIdx.y * per, v1 = min(NV, v0 + per);
   const float c = rj.c;
-#pragma unroll 1
-  for (int which = 0; which < 2; ++which) {
-    const long long r = (long long)b * rps + (which ? rj.nT + i : i);
-    const void* row = row_ptr<DT>(rj, r);
-    const bool aligned = (((size_t)row) & 15) == 0;
-    const float mc = rj.out[r].mc;
-    u64 s = 0;
-    sweep_range<DT, PT>(row, V, aligned, v0, v1, [&](const float(&x)[8], int) {
+  // both rows of the position in one loop: 8 independent 16-byte loads in flight per thread
+  const long long r1 = (long long)b * rps + i, r2 = (long long)b * rps + rj.nT + i;
+  const void* prow = row_ptr<DT>(rj, r1);
+  const void* qrow = row_ptr<DT>(rj, r2);
+  const bool pal = (((size_t)prow) & 15) == 0, qal = (((size_t)qrow) & 15) == 0;
+  const float mcp = rj.out[r1].mc, mcq = rj.out[r2].mc;
+  u64 sp = 0, sq = 0;
+  constexpr int NQ = (DT == DT_F32) ? 2 : 4;  // vectors of each row in flight per thread (raw, still packed)
+  for (int v = v0 + threadIdx.x; v < v1; v += NQ * PT) {
+    Raw8<DT> rp[NQ], rq[NQ];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) s += fix40(cweight(x[k], c, mc));
-    });
-    s = block_sum_u64(s, sh64);
-    if (threadIdx.x == 0 && s) atomicAdd(&ws.acc[r], s);
+    for (int q = 0; q < NQ; ++q) {
+      const int vv = min(v + q * PT, v1 - 1);
+      rp[q] = load_raw8<DT>(prow, vv, V, pal);
+      rq[q] = load_raw8<DT>(qrow, vv, V, qal);
+    }
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+      if (v + q * PT < v1) {
+        float x[8];
+        unpack8<DT>(rp[q], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sp += fix40(cweight(x[k], c, mcp));
+        unpack8<DT>(rq[q], x);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) sq += fix40(cweight(x[k], c, mcq));
+      }
+    }
+  }
+  sp = block_sum_u64(sp, sh64);
+  sq = block_sum_u64(sq, sh64);
+  if (threadIdx.x == 0) {
+    if (sp) atomicAdd(&ws.acc[r1], sp);
+    if (sq) atomicAdd(&ws.acc[r2], sq);
   }
   if (threadIdx.x == 0) {
     __threadfence();
@@ -295,6 +317,8 @@ __global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, Hybrid
   if (sh_last && threadIdx.x < 32) {
     __threadfence();
     decide_sequence<DT>(job, ws, b);
+  }
+  __syncthreads();
   }
 }
 
@@ -439,30 +463,35 @@ __device__ __forceinline__ void partial_loop(const void* prowp, const void* qrow
     return s;
   };
   constexpr int WPB = PT / 32;
-  int seg = s0 + w;
-  for (; seg + WPB < s1; seg += 2 * WPB) {
-    const int va = seg * 32 + lane, vb = (seg + WPB) * 32 + lane;
-    float xpa[8], xqa[8], xpb[8], xqb[8];
-    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
-    load8<DT>(prowp, min(vb, NV - 1), V, pal, xpb);
-    if (RESID) {
-      load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
-      load8<DT>(qrowp, min(vb, NV - 1), V, qal, xqb);
+  constexpr int NS = (DT == DT_F32) ? 2 : 4;  // segments in flight per warp (raw, still packed loads)
+  for (int seg = s0 + w; seg < s1; seg += NS * WPB) {
+    Raw8<DT> rpv[NS], rqv[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int vv = min((seg + q * WPB) * 32 + lane, NV - 1);
+      rpv[q] = load_raw8<DT>(prowp, vv, V, pal);
+      if (RESID) rqv[q] = load_raw8<DT>(qrowp, vv, V, qal);
     }
-    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
-    u64 sb = (vb < NV) ? seg_sum(xpb, xqb, vb) : 0ull;
-    sa = warp_sum_u64(sa);
-    sb = warp_sum_u64(sb);
-    if (lane == 0) { part[seg] = sa; part[seg + WPB] = sb; tot += sa + sb; }
-  }
-  for (; seg < s1; seg += WPB) {
-    const int va = seg * 32 + lane;
-    float xpa[8], xqa[8];
-    load8<DT>(prowp, min(va, NV - 1), V, pal, xpa);
-    if (RESID) load8<DT>(qrowp, min(va, NV - 1), V, qal, xqa);
-    u64 sa = (va < NV) ? seg_sum(xpa, xqa, va) : 0ull;
-    sa = warp_sum_u64(sa);
-    if (lane == 0) { part[seg] = sa; tot += sa; }
+    u64 sums[NS];
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int sg = seg + q * WPB, vv = sg * 32 + lane;
+      sums[q] = 0;
+      if (sg < s1 && vv < NV) {
+        float xp[8], xq[8];
+        unpack8<DT>(rpv[q], xp);
+        if (RESID) unpack8<DT>(rqv[q], xq);
+        sums[q] = seg_sum(xp, xq, vv);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < NS; ++q) {
+      const int sg = seg + q * WPB;
+      if (sg < s1) {  // warp-uniform
+        const u64 sa = warp_sum_u64(sums[q]);
+        if (lane == 0) { part[sg] = sa; tot += sa; }
+      }
+    }
   }
 }
 

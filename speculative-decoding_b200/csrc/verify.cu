@@ -1295,7 +1295,7 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws, int B
   const RowJob& rj = dj.rj;
   const bool masked = rj.top_k > 0 || rj.use_p;
   plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
-  if (!masked && dj.gamma > 0) exact_rows_kernel<DT><<<dim3((unsigned)(B * dj.gamma), CH), PT, 0, st>>>(dj, ws);
+  if (!masked && dj.gamma > 0) exact_rows_kernel<DT><<<dim3((unsigned)B, CH), PT, 0, st>>>(dj, ws);  // tasks are looped over
   const dim3 grid((unsigned)B, CH);
   if (masked) {
     if (dj.greedy) sample_partial_kernel<DT, true, true><<<grid, PT, 0, st>>>(dj, ws);
