@@ -55,6 +55,28 @@ __device__ __forceinline__ float cexp2_le(float t) {
 }
 // weight of logit z (<= row max m) under (c, mc): exp2(z*c - m*c), one rounding in the exponent argument
 __device__ __forceinline__ float cweight(float z, float c, float mc) { return cexp2_le(__fmaf_rn(z, c, -mc)); }
+// Two canonical weights per instruction stream: Blackwell's packed fp32x2 FMA/ADD (SASS FFMA2 / FADD2 /
+// FMUL2, sm_100+) are IEEE round-to-nearest per component, so the results are bit-identical to two
+// cweight() calls while the polynomial costs ~7 instead of 12 issue slots per element.
+__device__ __forceinline__ float2 cweight2(float2 z, float2 c, float2 negmc) {
+  float2 t = __ffma2_rn(z, c, negmc);
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 r = __fadd2_rn(t, magic);
+  const float2 fi = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));  // == r - magic
+  const float2 f = __ffma2_rn(fi, make_float2(-1.0f, -1.0f), t);              // == t - fi (exact product)
+  float2 p = make_float2(SPECDEC_C5, SPECDEC_C5);
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_C4, SPECDEC_C4));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_C3, SPECDEC_C3));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_C2, SPECDEC_C2));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_C1, SPECDEC_C1));
+  p = __ffma2_rn(p, f, make_float2(1.0f, 1.0f));
+  float2 e;
+  e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
+  e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return e;
+}
 __device__ __forceinline__ u64 fix40(float x) { return __float2ull_rz(__fmul_rn(x, 1099511627776.0f)); }
 __device__ __forceinline__ u64 fix60(float x) { return __float2ull_rz(__fmul_rn(x, 1152921504606846976.0f)); }
 __device__ __forceinline__ unsigned u24_of(float u) {

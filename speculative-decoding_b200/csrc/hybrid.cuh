@@ -280,6 +280,7 @@ __global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, Hybrid
   const void* qrow = row_ptr<DT>(rj, r2);
   const bool pal = (((size_t)prow) & 15) == 0, qal = (((size_t)qrow) & 15) == 0;
   const float mcp = rj.out[r1].mc, mcq = rj.out[r2].mc;
+  const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mcp, -mcq);
   u64 sp = 0, sq = 0;
   constexpr int NQ = (DT == DT_F32) ? 2 : 4;  // vectors of each row in flight per thread (raw, still packed)
   for (int v = v0 + threadIdx.x; v < v1; v += NQ * PT) {
@@ -293,13 +294,15 @@ __global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, Hybrid
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
       if (v + q * PT < v1) {
-        float x[8];
-        unpack8<DT>(rp[q], x);
+        float xp[8], xq[8];
+        unpack8<DT>(rp[q], xp);
+        unpack8<DT>(rq[q], xq);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) sp += fix40(cweight(x[k], c, mcp));
-        unpack8<DT>(rq[q], x);
-#pragma unroll
-        for (int k = 0; k < 8; ++k) sq += fix40(cweight(x[k], c, mcq));
+        for (int k = 0; k < 8; ++k) {  // (target, drafter) logit of the same token as one fp32x2 pair
+          const float2 e = cweight2(make_float2(xp[k], xq[k]), c2, nmc2);
+          sp += fix40(e.x);
+          sq += fix40(e.y);
+        }
       }
     }
   }
@@ -441,6 +444,7 @@ __device__ __forceinline__ void partial_loop(const void* prowp, const void* qrow
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int NV = (V + 7) >> 3;
   const float mcp = rp.mc, mcq = rq.mc, invp = rp.inv, invq = rq.inv;
+  const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mcp, -mcq), inv2 = make_float2(invp, invq);
   auto seg_sum = [&](const float(&xp)[8], const float(&xq)[8], int v) -> u64 {
     u64 s = 0;
 #pragma unroll
@@ -449,9 +453,10 @@ __device__ __forceinline__ void partial_loop(const void* prowp, const void* qrow
       float val;
       if (RESID) {
         const bool kp = !MASKED || kept(rp, xp[k], j), kq = !MASKED || kept(rq, xq[k], j);
-        const float P = __fmul_rn(kp ? cweight(xp[k], c, mcp) : 0.0f, invp);
-        const float Q = __fmul_rn(kq ? cweight(xq[k], c, mcq) : 0.0f, invq);
-        val = fmaxf(__fsub_rn(P, Q), 0.0f);
+        float2 e = cweight2(make_float2(xp[k], xq[k]), c2, nmc2);
+        if (MASKED) { e.x = kp ? e.x : 0.0f; e.y = kq ? e.y : 0.0f; }
+        const float2 PQ = __fmul2_rn(e, inv2);
+        val = fmaxf(__fsub_rn(PQ.x, PQ.y), 0.0f);
         s += fix60(val);
       } else {
         const bool kp = !MASKED || kept(rp, xp[k], j);

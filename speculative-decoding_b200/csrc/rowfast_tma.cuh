@@ -12,7 +12,7 @@
 
 constexpr int TS_CONSUMERS = 256;
 constexpr int TS_THREADS = TS_CONSUMERS + 32;
-constexpr int TS_STAGES = 8;
+constexpr int TS_STAGES = 6;
 constexpr int TS_STAGE_BYTES = 8192;
 constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES;
 
@@ -35,11 +35,19 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity) {
       "bra WAIT_LOOP;\n\t"
       "DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
-__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
+__device__ __forceinline__ unsigned long long l2_evict_first_policy() {
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  return pol;
+}
+// streaming read: the logits are consumed once by this kernel, so they are marked evict-first in L2
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, unsigned bytes, void* bar,
+                                             unsigned long long policy) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+      : "memory");
 }
 
 // online (max, sum) update with one 16-byte vector
@@ -70,14 +78,20 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
     }
     const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
     if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
-    const float mc = __fmul_rn(m, c);
+    // packed fp32x2 (FFMA2 / FADD2): half the issue slots for the exponent arguments and the accumulation
+    const float2 c2 = make_float2(c, c), nmc2 = make_float2(-__fmul_rn(m, c), -__fmul_rn(m, c));
+    float2 acc = make_float2(s, 0.0f);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
+    for (int k = 0; k < 4; ++k) {
+      const float2 t = __ffma2_rn(make_float2(x[2 * k], x[2 * k + 1]), c2, nmc2);
+      acc = __fadd2_rn(acc, make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+    }
+    s = __fadd_rn(acc.x, acc.y);
   }
 }
 
 template <int DT>
-__global__ void __launch_bounds__(TS_THREADS, 3) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
+__global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
   const RowJob& job = dj.rj;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
@@ -97,6 +111,7 @@ __global__ void __launch_bounds__(TS_THREADS, 3) rowfast_tma_kernel(DecideJob dj
     if (lane == 0) {
       int stage = 0;
       unsigned phase = 0;
+      const unsigned long long policy = l2_evict_first_policy();
       for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
         const char* base = (const char*)row_ptr<DT>(job, r);
         for (int k = 0; k < nst; ++k) {
@@ -104,7 +119,7 @@ __global__ void __launch_bounds__(TS_THREADS, 3) rowfast_tma_kernel(DecideJob dj
           const unsigned off = (unsigned)k * TS_STAGE_BYTES;
           const unsigned nb = min((unsigned)TS_STAGE_BYTES, row_bytes - off);
           mbar_expect_tx(&full_bar[stage], nb);
-          tma_bulk_g2s(ring + stage * TS_STAGE_BYTES, base + off, nb, &full_bar[stage]);
+          tma_bulk_g2s(ring + stage * TS_STAGE_BYTES, base + off, nb, &full_bar[stage], policy);
           if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
         }
       }

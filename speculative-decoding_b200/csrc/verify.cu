@@ -1281,7 +1281,7 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
       if (e != cudaSuccess) return e;
       attr_set[DT] = true;
     }
-    const long long cap = (long long)ctas_per_sm * num_sms();
+    const long long cap = (long long)(ctas_per_sm + 1) * num_sms();
     rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   } else {
     rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
