@@ -98,6 +98,7 @@ SPECDEC_API int specdec_verify(const void* target_logits, const void* draft_logi
  * before the row-statistics kernel, between the two kernels and after the decide kernel. */
 SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end);
 /* Test hooks: "force_ldg"=1 makes the row kernel use vectorised LDG instead of the TMA pipeline;
+ * "no_fast_nucleus"=1 / "no_fast_ngram"=1 force the exact-only kernels for top-p rows / greedy n-gram verify;
  * "no_overlap"=0 enables an optional two-stream half-batch pipelining of the verify step (default 1 = off:
  * measured no gain on B200, the step is instruction-issue bound). */
 SPECDEC_API int specdec_set_option(const char* name, int value);

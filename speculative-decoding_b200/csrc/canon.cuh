@@ -94,6 +94,17 @@ __device__ __forceinline__ u64 scale_q32(u64 S, u64 q32) {
   u64 hi = __umul64hi(S, q32), lo = S * q32;
   return (hi << 32) | (lo >> 32);
 }
+// sum of the 8 fixed-point weights of one vector (packed fp32x2 evaluation, bit-identical to scalar)
+__device__ __forceinline__ u64 sum_fix40_8(const float (&x)[8], float c, float mc) {
+  const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mc, -mc);
+  u64 s = 0;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 e = cweight2(make_float2(x[2 * k], x[2 * k + 1]), c2, nmc2);
+    s += fix40(e.x) + fix40(e.y);
+  }
+  return s;
+}
 // order-preserving float -> uint32 key
 __device__ __forceinline__ unsigned fkey(float z) {
   unsigned b = __float_as_uint(__fadd_rn(z, 0.0f));  // -0.0 -> +0.0 so that key order == float order

@@ -201,22 +201,12 @@ __global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
   plan_sequence<DT>(job, ws, b);
 }
 
-// called by thread `tid0` of a row kernel after it wrote RowOut of row r; returns the sequence id
-// whose rows are now all complete (then ONE warp must call plan_sequence) or -1
-__device__ __forceinline__ int row_done(const RowJob& rj, const HybridWs& ws, long long r) {
-  __threadfence();
-  const int rps = rj.nT + rj.nD;
-  const int b = (int)(r / rps);
-  return (atomicAdd(&ws.rows_done[b], 1) == rps - 1) ? b : -1;
-}
-
 // ---------------------------------------------------------------------------------------------
 // row kernel, vectorised-LDG version (fp32 rows, unaligned rows)
 // ---------------------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs ws) {
   __shared__ float shf[33];
-  __shared__ int sh_seq;
   const RowJob& job = dj.rj;
   const long long r = blockIdx.x;
   const void* row = row_ptr<DT>(job, r);
@@ -245,14 +235,133 @@ __global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs w
     float t = (lane < FT / 32) ? shf[lane] : 0.0f;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-    int seq = -1;
     if (lane == 0) {
       RowOut o;
       o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, t);
       o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
       job.out[r] = o;
     }
-    (void)seq;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// n-gram-assisted verify, greedy processor (ngram_assisted/ngram_assisted.py:114-141 with GreedyProcessor):
+// every decision is "draft == argmax(p_i)" and the next token is argmax(p_n), so no normaliser is needed
+// for the decisions at all.  rowfast_argmax_kernel = the fast row kernel + (first index of the row
+// maximum, second largest distinct value).  The canonical arg-max is over the weights e_j = cexp2(t_j);
+// it equals the arg-max over the logits whenever the runner-up is >= 4e-6 below the maximum in exponent
+// units (20x the polynomial's error) -- always for bf16/fp16 logits; rows that are closer are redone
+// exactly by ngram_greedy_decide_kernel.
+// ---------------------------------------------------------------------------------------------
+template <int DT>
+__global__ void __launch_bounds__(FT, 2) rowfast_argmax_kernel(RowJob job) {
+  __shared__ float shf[33];
+  __shared__ unsigned shu[33];
+  const long long r = blockIdx.x;
+  const void* row = row_ptr<DT>(job, r);
+  const bool aligned = (((size_t)row) & 15) == 0;
+  const int V = job.V, NV = (V + 7) >> 3;
+  const float c = job.c;
+  float m = -INFINITY, s = 0.0f, s2 = -INFINITY;
+  int idx = 0x7FFFFFFF;
+  sweep_range<DT, FT>(row, V, aligned, 0, NV, [&](const float(&x)[8], int j0) {
+    const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+    if (vm > s2) {  // rare after the first few vectors
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float xv = x[k];
+        if (xv > m) {
+          s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, xv), c)));
+          s2 = m; m = xv; idx = j0 + k;
+        } else if (xv < m && xv > s2) {
+          s2 = xv;
+        }
+      }
+    }
+    const float mc = __fmul_rn(m, c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
+  });
+  const float M = block_max_f(m, shf);
+  const unsigned first = block_min_u32((m == M) ? (unsigned)idx : 0xFFFFFFFFu, shu);
+  const float second = block_max_f((m < M) ? m : s2, shf);
+  s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, M), c))) : 0.0f;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (lane == 0) shf[w] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = (lane < FT / 32) ? shf[lane] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    if (lane == 0) {
+      const bool amb = !(M > -INFINITY) || !(M < INFINITY) || first >= (unsigned)V ||
+                       (second > -INFINITY && !(__fmul_rn(__fsub_rn(M, second), c) >= 4e-6f));
+      RowOut o;
+      o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, t);
+      o.cut = -INFINITY; o.jcut = V; o.flags = 0;
+      o.Sfix = (u64)first | (amb ? (1ull << 32) : 0ull);
+      job.out[r] = o;
+    }
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(PT, 4) ngram_greedy_decide_kernel(DecideJob job, HybridWs ws) {
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ int shi[33];
+  __shared__ long long s_res;
+  __shared__ long long s_tok[66];
+  const RowJob& rj = job.rj;
+  const int b = blockIdx.x, g = job.gamma, V = rj.V, nT = rj.nT;
+  const RowOut* ro = rj.out + (long long)b * nT;
+  const Scratch scr{ws.part + (size_t)b * ws.nseg_pad, sh64, shf, shi, &s_res};
+  for (int i = threadIdx.x; i < nT; i += blockDim.x) {
+    const u64 v = ro[i].Sfix;
+    s_tok[i] = ((v >> 32) & 1ull) ? -1ll : (long long)(v & 0xFFFFFFFFull);
+  }
+  __syncthreads();
+  for (int i = 0; i < nT; ++i) {  // block-uniform: exact arg-max for the (rare) near-tie rows
+    if (s_tok[i] < 0) {
+      const long long x = sample_p_row<DT>(row_ptr<DT>(rj, (long long)b * nT + i), ro[i], V, rj.c, true, 0.0f, scr);
+      if (threadIdx.x == 0) s_tok[i] = x;
+      __syncthreads();
+    }
+  }
+  if (threadIdx.x == 0) {
+    const long long* toks = job.draft_tokens + (long long)b * g;
+    int n = g;
+    for (int i = 0; i < g; ++i) {
+      const int tok = (int)min(max(toks[i], 0ll), (long long)V - 1);
+      const int a = (s_tok[i] == toks[i]) ? 1 : 0;
+      job.mask[(long long)b * g + i] = (unsigned char)a;
+      const float z = load1<DT>(row_ptr<DT>(rj, (long long)b * nT + i), tok);
+      job.p_tok[(long long)b * g + i] = exp2f(__fmaf_rn(z, rj.c, -ro[i].mc)) * ro[i].inv;
+      job.q_tok[(long long)b * g + i] = 0.0f;
+      if (!a && n == g) n = i;
+    }
+    int fs = -1;
+    for (int i = 0; i < n && fs < 0; ++i)
+      for (int k = 0; k < job.n_stop; ++k)
+        if (toks[i] == job.stop[k]) { fs = i; break; }
+    const long long x = (n < nT) ? s_tok[n] : -1ll;  // argmax(p_n), or the bonus row; -1 without a bonus row
+    job.n_acc[b] = n;
+    job.first_stop[b] = fs;
+    job.next_tok[b] = x;
+    if (job.next_prob) {
+      float np = 0.0f;
+      if (x >= 0) np = exp2f(__fmaf_rn(load1<DT>(row_ptr<DT>(rj, (long long)b * nT + n), (int)x), rj.c, -ro[n].mc)) * ro[n].inv;
+      job.next_prob[b] = np;
+    }
+    if (job.packed) {
+      int* pk = job.packed + (long long)b * (g + 2);
+      pk[0] = n;
+      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
+      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
+      pk[1 + n] = (int)x;
+    }
   }
 }
 

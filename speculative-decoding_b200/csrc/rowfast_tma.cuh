@@ -96,7 +96,6 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
   __shared__ float sh_m[2][8], sh_s[2][8];
-  __shared__ int sh_seq[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
   const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
@@ -156,7 +155,6 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
     if (lane == 0) { sh_m[par][warp] = wm; sh_s[par][warp] = s; }
     asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
     if (warp == 0) {
-      int seq = -1;
       if (lane == 0) {
         float M = sh_m[par][0];
 #pragma unroll
@@ -170,7 +168,6 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
         o.cut = -INFINITY; o.jcut = job.V; o.flags = 0; o.Sfix = 0;
         job.out[r] = o;
       }
-      (void)seq;
     }
   }
 }

@@ -424,10 +424,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
     u64 Sfix = 0;
     if (!masked) {
       u64 s = 0;
-      sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
-#pragma unroll
-        for (int k = 0; k < 8; ++k) s += fix40(cweight(x[k], c, mc));
-      });
+      sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) { s += sum_fix40_8(x, c, mc); });
       Sfix = block_sum_u64(s, sh64);
     } else {
       const float c1 = job.c1;
@@ -445,7 +442,6 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
       tau[3] = block_min_f(tmax, shf);
       int L = -1;
       u64 S1 = 0;
-      float band_lo = -INFINITY, band_hi = INFINITY;  // pure-nucleus band; otherwise [tau[L], +inf)
       u64 band_G = 0;
       if (HK) {
         if (job.top_k <= RS_NT) {
@@ -484,10 +480,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
         if (threadIdx.x == 0) s_count = 0;
         __syncthreads();
         auto emit = [&](const float(&x)[8], int v) {
-          if (sa) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) *sa += fix40(cweight(x[k], c1, mc1));  // (-inf padding contributes 0)
-          }
+          if (sa) *sa += sum_fix40_8(x, c1, mc1);  // (-inf padding contributes 0)
           compact_vec(x, v, th, up, V, cz, cj, &s_count, CAP);
         };
         for (int base = (threadIdx.x >> 5) << 5; base < NVr; base += 4 * RS_NT) {  // warp-uniform
@@ -1143,6 +1136,7 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 // host side
 // ---------------------------------------------------------------------------------------------
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
+static int g_no_fast_ngram = 0;    // test hook: specdec_set_option("no_fast_ngram", 1)
 static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_sms = 0;
@@ -1444,6 +1438,21 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
   dj.q_tok = q_tok; dj.first_stop = first_stop; dj.next_prob = next_prob; dj.packed = packed;
   dj.lane_sample = 0x10000;
   cudaStream_t st = (cudaStream_t)stream;
+  const bool masked_mode = dj.rj.top_k > 0 || dj.rj.use_p;
+  if (ngram && dj.greedy && !masked_mode && !g_no_fast_ngram) {
+    // greedy n-gram verify: arg-max per row from the fast row kernel, no exact pass (hybrid.cuh)
+    HybridWs ws = ws_pointers(wl, workspace, B, dj.rj.R);
+    if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+    DISPATCH_DT(dtype, {
+      rowfast_argmax_kernel<DT><<<(unsigned)dj.rj.R, FT, 0, st>>>(dj.rj);
+      if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+      ngram_greedy_decide_kernel<DT><<<B, PT, 0, st>>>(dj, ws);
+      cudaError_t e = cudaGetLastError();
+      if (e != cudaSuccess) return (int)e;
+    });
+    if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+    return 0;
+  }
   if (ngram) {  // per-position sample(p_i) comparisons: exact statistics for every row, one CTA per sequence
     if (g_ev[0]) cudaEventRecord(g_ev[0], st);
     DISPATCH_DT(dtype, {
@@ -1469,6 +1478,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
   if (!strcmp(name, "no_overlap")) { g_no_overlap = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
+  if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
   return SPECDEC_ERR_ARG;
 }
 

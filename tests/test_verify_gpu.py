@@ -302,3 +302,35 @@ def test_randomised_configurations(oracle_mod):
             _assert_same(o, r)
         except AssertionError as e:
             raise AssertionError(f"config {it}: B={B} gamma={gamma} V={V} {dtype} {mode} flags={flags} sigma={sigma} {kind}: {e}")
+
+
+def test_ngram_greedy_fast_path_and_near_ties(oracle_mod):
+    """greedy n-gram verify takes the arg-max from the fast row kernel; rows whose two largest logits are
+    within the polynomial's resolution fall back to the exact arg-max.  Both equal the oracle."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g, V = 6, 3, 50000
+    gen = torch.Generator().manual_seed(8)
+    t = 2.0 * torch.randn(B, g + 1, V, generator=gen)
+    # near ties: runner-up one ulp (fp32) below / equal to the maximum, at a LOWER and a HIGHER index
+    for b in range(B):
+        for i in range(g + 1):
+            mx = float(t[b, i].max())
+            j = int(t[b, i].argmax())
+            k = (j + 1234 * (b + 1)) % V if (b + i) % 2 else (j - 777 * (i + 1)) % V
+            t[b, i, k] = float(np.nextafter(np.float32(mx), np.float32(-1e9))) if b % 3 else mx
+    for dtype in (torch.float32, torch.bfloat16):
+        tt = t.to(dtype)
+        toks = tt[:, :g].float().argmax(-1)
+        toks[1, 1] = 3
+        ua = torch.zeros(B, g); us = torch.zeros(B)
+        o = oracle_mod.verify(tt, None, toks, ua, us, greedy=True, flags=F_NGRAM)
+        r1 = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)
+        assert lib.specdec_set_option(b"no_fast_ngram", 1) == 0
+        try:
+            r2 = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)
+        finally:
+            lib.specdec_set_option(b"no_fast_ngram", 0)
+        _assert_same(o, r1, ngram=True)
+        _assert_same(o, r2, ngram=True)
+        assert torch.equal(r1.next_token, r2.next_token)
