@@ -520,7 +520,32 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
       u64 S_above = 0;
       if (HK) {
         if (L >= 0) {
-          n = collect(tau[L], INFINITY, nullptr);
+          // Candidates (z >= th) can only sit in the slices of threads whose own maximum is >= th -- about k of
+          // the 512 threads.  Instead of a second sweep over the whole row, each warp re-reads just those
+          // slices (vector v = t + l*RS_NT of thread t: one gather per 32 vectors) and compacts the hits.
+          const float th = tau[L];
+          const int NVr = (V + 7) >> 3, lane = threadIdx.x & 31;
+          if (threadIdx.x == 0) s_count = 0;
+          __syncthreads();
+          unsigned bal = __ballot_sync(0xffffffffu, tmax >= th);
+          while (bal) {
+            const int src = __ffs(bal) - 1;
+            bal &= bal - 1;
+            const int tbase = (threadIdx.x & ~31) + src;
+            for (int l0 = 0; tbase + l0 * RS_NT < NVr; l0 += 32) {  // warp-uniform
+              const int v = tbase + (l0 + lane) * RS_NT;
+              float x[8];
+              load8<DT>(row, min(v, NVr - 1), V, aligned, x);
+              if (v >= NVr) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) x[k] = -INFINITY;
+              }
+              compact_vec(x, v, th, INFINITY, V, cz, cj, &s_count, CAP);
+            }
+          }
+          __syncthreads();
+          n = s_count;
+          __syncthreads();
           if (n > CAP || n < job.top_k || n == 0) L = -1;
         }
       } else {
