@@ -56,6 +56,11 @@ def lib():
             fn = getattr(_lib, name)  # AttributeError if the .so does not export a declared symbol
             fn.restype = res
             fn.argtypes = args
+        # tuning / test hooks of the library, e.g. SPECDEC_OPTS="no_overlap=0,no_fused_tail=1" (see specdec_set_option)
+        for kv in filter(None, os.environ.get("SPECDEC_OPTS", "").split(",")):
+            k, v = kv.split("=")
+            if _lib.specdec_set_option(k.strip().encode(), int(v)) != 0:
+                raise RuntimeError(f"SPECDEC_OPTS: unknown option {k!r}")
     return _lib
 
 

@@ -26,6 +26,7 @@ constexpr int PT = 256;   // threads, chunk kernels
 constexpr int CH = 8;     // CTAs per row (pair) in exact_rows / sample_partial
 constexpr int ST_ACCEPT = 0, ST_REJECT = 1, ST_AMBIG = 2, ST_EXACTROW = 3, ST_NEED = 4;
 constexpr float MARGIN = 1e-3f;
+constexpr int SAMP_N = 8;  // ints per sequence in HybridWs::samp
 
 struct HybridWs {
   u64* acc;               // [R]  canonical Sfix of task rows
@@ -35,11 +36,16 @@ struct HybridWs {
   u64* part;              // [B][nseg_pad]
   u64* tot;               // [B]
   u64* best;              // [B]  greedy: (value bits << 32) | ~index
-  int* samp;              // [B][4]: n, mode, p-row position, unused
+  int* samp;              // [B][SAMP_N]: n, mode, p-row position, bits of mc of the p row, of the q row
   int* rows_done;         // [B]  rows of the sequence whose statistics are written
   int* seq_tasks;         // [B]  number of exact tasks of the sequence
   int* exact_done;        // [B]
   int* part_done;         // [B]
+  u64* acc2;              // [B][2]  fused tail: canonical Sfix of the deciding row pair
+  int* fin_done;          // [B]     fused tail: CTAs whose partial sums are in acc2
+  int* decided;           // [B]     fused tail: set once CTA 0 of the group has decided the sequence
+  int* ticket;            // [2]     fused tail: logical CTA ids in dispatch order (one counter per half batch)
+  int fused;              // plan: the first sure reject is handled by tail_fused_kernel, not as an exact task
   int nseg_pad;
 };
 
@@ -112,7 +118,12 @@ __device__ void decide_sequence(const DecideJob& job, const HybridWs& ws, int b)
         if (toks[i] == job.stop[k]) { fs = i; break; }
     job.n_acc[b] = n;
     job.first_stop[b] = fs;
-    ws.samp[b * 4 + 0] = n; ws.samp[b * 4 + 1] = mode; ws.samp[b * 4 + 2] = prow;
+    ws.samp[b * SAMP_N + 0] = n; ws.samp[b * SAMP_N + 1] = mode; ws.samp[b * SAMP_N + 2] = prow;
+    if (mode) {  // one record read gives tail_fused_kernel everything it needs to start streaming
+      const int rps = rj.nT + rj.nD;
+      ws.samp[b * SAMP_N + 3] = __float_as_int(rj.out[(long long)b * rps + prow].mc);
+      ws.samp[b * SAMP_N + 4] = (mode == 2) ? __float_as_int(rj.out[(long long)b * rps + rj.nT + prow].mc) : 0;
+    }
     if (mode == 0) {  // nothing to sample (all accepted, no bonus token)
       job.next_tok[b] = -1;
       if (job.next_prob) job.next_prob[b] = 0.0f;
@@ -172,14 +183,16 @@ __device__ void plan_sequence(const DecideJob& job, const HybridWs& ws, int b) {
     const unsigned rej = __ballot_sync(0xffffffffu, i < g && !exact_row && st == ST_REJECT);
     bool need = (i < g) && !exact_row && (st == ST_AMBIG);
     if (!have_reject && rej) {
-      if (lane == __ffs(rej) - 1) need = true;
+      if (!ws.fused && lane == __ffs(rej) - 1) need = true;
       have_reject = true;
     }
     if (i < g) {
       if (need) {
         st |= ST_NEED;
-        const int t = atomicAdd(ws.ntasks, 1);
-        ws.tasks[t] = b * g + i;
+        if (!ws.fused) {
+          const int t = atomicAdd(ws.ntasks, 1);
+          ws.tasks[t] = b * g + i;
+        }
       }
       ws.status[(long long)b * g + i] = (unsigned char)st;
     }
@@ -484,7 +497,7 @@ __device__ void finalize_sequence(const DecideJob& job, const HybridWs& ws, int 
                                   long long* s_res) {
   const RowJob& rj = job.rj;
   const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
-  const int n = __ldcg(&ws.samp[b * 4 + 0]), mode = __ldcg(&ws.samp[b * 4 + 1]), prow = __ldcg(&ws.samp[b * 4 + 2]);
+  const int n = __ldcg(&ws.samp[b * SAMP_N + 0]), mode = __ldcg(&ws.samp[b * SAMP_N + 1]), prow = __ldcg(&ws.samp[b * SAMP_N + 2]);
   const bool greedy = job.greedy != 0;
   const float us = job.u_sample ? job.u_sample[b]
                                 : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
@@ -622,7 +635,7 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
   const RowJob& rj = job.rj;
   const int b = blockIdx.x, ch = blockIdx.y, V = rj.V, rps = rj.nT + rj.nD;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int mode = ws.samp[b * 4 + 1], prow = ws.samp[b * 4 + 2];
+  const int mode = ws.samp[b * SAMP_N + 1], prow = ws.samp[b * SAMP_N + 2];
   if (mode == 0) return;
   const long long r1 = (long long)b * rps + prow;
   const void* prowp = row_ptr<DT>(rj, r1);
@@ -668,3 +681,5 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
     finalize_sequence<DT>(job, ws, b, sh64, shf, shi, &s_res);
   }
 }
+
+#include "tail_fused.cuh"

@@ -1164,6 +1164,7 @@ static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / 
 static int g_no_fast_ngram = 0;    // test hook: specdec_set_option("no_fast_ngram", 1)
 static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
+static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 static int g_sms = 0;
 static int num_sms() {
   if (g_sms == 0) {
@@ -1244,12 +1245,12 @@ static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   size_t o = 0;
   w.rowout = o; o = al256(o + (size_t)R * sizeof(RowOut));
   w.zero = o;
-  o += (size_t)R * 8 + (size_t)B * 8 * 2 + 8 + (size_t)B * 4 * 4;
+  o += (size_t)R * 8 + (size_t)B * 8 * 2 + (size_t)B * 8 * 2 + 64 + 64 + (size_t)B * 4 * 6;
   w.zero_bytes = o - w.zero;
   o = al256(o);
   w.tasks = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1) * 4);
   w.status = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1));
-  w.samp = o; o = al256(o + (size_t)B * 16);
+  w.samp = o; o = al256(o + (size_t)B * 4 * SAMP_N);
   w.part = o; o = al256(o + (size_t)B * w.nseg_pad * 8);
   w.total = o;
   return w;
@@ -1260,11 +1261,16 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   h.acc = (u64*)(base + w.zero);
   h.tot = h.acc + R;
   h.best = h.tot + B;
-  h.ntasks = (int*)(h.best + B);
-  h.rows_done = h.ntasks + 2;
+  h.acc2 = h.best + B;
+  h.ntasks = (int*)(h.acc2 + 2 * B);
+  h.ticket = h.ntasks + 16;
+  h.rows_done = h.ticket + 16;
   h.seq_tasks = h.rows_done + B;
   h.exact_done = h.seq_tasks + B;
   h.part_done = h.exact_done + B;
+  h.fin_done = h.part_done + B;
+  h.decided = h.fin_done + B;
+  h.fused = 0;
   h.tasks = (int*)(base + w.tasks);
   h.status = (unsigned char*)(base + w.status);
   h.samp = (int*)(base + w.samp);
@@ -1273,10 +1279,11 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   return h;
 }
 
-static int g_no_overlap = 1;  // half-batch pipelining on two streams is OFF by default (measured: no gain, the
-                              // step is issue-bound); specdec_set_option("no_overlap", 0) enables it
+static int g_chunks = 2;    // batch chunks pipelined on two streams (specdec_set_option("chunks", n); 1 = off)
+static int g_p1_ctas = 3;   // row-kernel CTAs per SM while a tail kernel of the previous chunk shares the SMs
+static int g_tf_ch = TF_CH_DEFAULT;  // CTAs per sequence of tail_fused_kernel
 static cudaStream_t g_aux_stream = nullptr;
-static cudaEvent_t g_ev_a1 = nullptr, g_ev_b1 = nullptr;
+static cudaEvent_t g_ev_a[8] = {nullptr}, g_ev_b1 = nullptr;
 
 // phase A: row statistics of the job's rows.  limit_ctas > 0 caps the persistent grid per SM.
 template <int DT>
@@ -1310,9 +1317,28 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
 
 // phase B: plan, exact sums of the deciding rows, sampling sweep + finalize
 template <int DT>
-static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws, int B, cudaStream_t st) {
+static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, int B, cudaStream_t st) {
   const RowJob& rj = dj.rj;
   const bool masked = rj.top_k > 0 || rj.use_p;
+  HybridWs ws = ws_in;
+  // fused tail (tail_fused.cuh): nch CTAs per sequence keep the canonical weights of the deciding row pair
+  // in shared memory; needs the slice of one CTA to fit
+  const int nch = g_tf_ch;
+  const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5), spc = (nseg + nch - 1) / nch;
+  const size_t tf_smem = (size_t)spc * TF_SEG_BYTES;
+  if (!masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail) {
+    ws.fused = 1;
+    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
+    cudaError_t e;
+    if (dj.greedy) {
+      if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+      tail_fused_kernel<DT, true><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
+    } else {
+      if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+      tail_fused_kernel<DT, false><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
+    }
+    return cudaGetLastError();
+  }
   plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
   if (!masked && dj.gamma > 0) exact_rows_kernel<DT><<<dim3((unsigned)B, CH), PT, 0, st>>>(dj, ws);  // tasks are looped over
   const dim3 grid((unsigned)B, CH);
@@ -1347,10 +1373,12 @@ static void sub_job(const DecideJob& dj, const HybridWs& ws, int b0, int nb, int
   if (dj.next_prob) o.next_prob = dj.next_prob + b0;
   if (dj.packed) o.packed = dj.packed + (size_t)b0 * (g + 2);
   w.acc = ws.acc + (size_t)b0 * rps; w.tot = ws.tot + b0; w.best = ws.best + b0;
+  w.acc2 = ws.acc2 + (size_t)b0 * 2; w.fin_done = ws.fin_done + b0; w.decided = ws.decided + b0;
+  w.ticket = ws.ticket + half;
   w.ntasks = ws.ntasks + half;
   w.tasks = ws.tasks + (size_t)b0 * (g > 0 ? g : 1);
   w.status = ws.status + (size_t)b0 * (g > 0 ? g : 1);
-  w.samp = ws.samp + (size_t)b0 * 4;
+  w.samp = ws.samp + (size_t)b0 * SAMP_N;
   w.rows_done = ws.rows_done + b0; w.seq_tasks = ws.seq_tasks + b0;
   w.exact_done = ws.exact_done + b0; w.part_done = ws.part_done + b0;
   w.part = ws.part + (size_t)b0 * ws.nseg_pad;
@@ -1363,33 +1391,40 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   HybridWs ws = ws_pointers(wl, workspace, B, rj.R);
   cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st);
   if (e != cudaSuccess) return e;
-  // Two half-batches pipelined on two streams: the HBM-bound row kernel of the second half overlaps the
-  // FMA-bound exact/sampling kernels of the first half.  Results do not depend on the split.
-  const bool split = !masked && dj.gamma > 0 && B >= 64 && !g_no_overlap;
-  if (split && !g_aux_stream) {
-    if ((e = cudaStreamCreateWithFlags(&g_aux_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&g_ev_a1, cudaEventDisableTiming)) != cudaSuccess) return e;
+  // Chunks of the batch pipelined on two streams: the HBM-bound row kernel of chunk i+1 overlaps the
+  // latency/issue-bound exact tail of chunk i.  Results do not depend on the split.
+  int C = g_chunks;
+  if (masked || dj.gamma == 0 || B < 64 * C || C > 8 || DT == DT_F32) C = 1;  // (fp32 rows: LDG row kernel, no gain)
+  if (C > 1 && !g_aux_stream) {
+    int lo = 0, hi = 0;
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if ((e = cudaStreamCreateWithPriority(&g_aux_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    for (int i = 0; i < 8; ++i)
+      if ((e = cudaEventCreateWithFlags(&g_ev_a[i], cudaEventDisableTiming)) != cudaSuccess) return e;
     if ((e = cudaEventCreateWithFlags(&g_ev_b1, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
   if (g_ev[0]) cudaEventRecord(g_ev[0], st);
-  if (!split) {
+  if (C == 1) {
     if ((e = launch_phase_a<DT>(dj, ws, B, 3, st)) != cudaSuccess) return e;
     if (g_ev[1]) cudaEventRecord(g_ev[1], st);
     if ((e = launch_phase_b<DT>(dj, ws, B, st)) != cudaSuccess) return e;
   } else {
-    const int B1 = B / 2, B2 = B - B1;
-    DecideJob d1, d2;
-    HybridWs w1, w2;
-    sub_job<DT>(dj, ws, 0, B1, 0, d1, w1);
-    sub_job<DT>(dj, ws, B1, B2, 1, d2, w2);
-    if ((e = launch_phase_a<DT>(d1, w1, B1, 3, st)) != cudaSuccess) return e;
-    cudaEventRecord(g_ev_a1, st);
-    cudaStreamWaitEvent(g_aux_stream, g_ev_a1, 0);
-    if ((e = launch_phase_b<DT>(d1, w1, B1, g_aux_stream)) != cudaSuccess) return e;
+    for (int i = 0; i < C; ++i) {
+      const int b0 = (int)((long long)B * i / C), b1 = (int)((long long)B * (i + 1) / C);
+      DecideJob d;
+      HybridWs w;
+      sub_job<DT>(dj, ws, b0, b1 - b0, i, d, w);
+      if ((e = launch_phase_a<DT>(d, w, b1 - b0, i == 0 ? 3 : g_p1_ctas - 1, st)) != cudaSuccess) return e;
+      if (i == C - 1) {
+        if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+        if ((e = launch_phase_b<DT>(d, w, b1 - b0, st)) != cudaSuccess) return e;
+      } else {
+        cudaEventRecord(g_ev_a[i], st);
+        cudaStreamWaitEvent(g_aux_stream, g_ev_a[i], 0);
+        if ((e = launch_phase_b<DT>(d, w, b1 - b0, g_aux_stream)) != cudaSuccess) return e;
+      }
+    }
     cudaEventRecord(g_ev_b1, g_aux_stream);
-    if ((e = launch_phase_a<DT>(d2, w2, B2, 2, st)) != cudaSuccess) return e;
-    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
-    if ((e = launch_phase_b<DT>(d2, w2, B2, st)) != cudaSuccess) return e;
     cudaStreamWaitEvent(st, g_ev_b1, 0);
   }
   if (g_ev[2]) cudaEventRecord(g_ev[2], st);
@@ -1501,9 +1536,13 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
 int specdec_set_option(const char* name, int value) {
   if (!name) return SPECDEC_ERR_ARG;
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
-  if (!strcmp(name, "no_overlap")) { g_no_overlap = value; return 0; }
+  if (!strcmp(name, "no_overlap")) { g_chunks = value ? 1 : 2; return 0; }
+  if (!strcmp(name, "chunks")) { if (value < 1 || value > 8) return SPECDEC_ERR_ARG; g_chunks = value; return 0; }
+  if (!strcmp(name, "p1_ctas")) { if (value < 1 || value > 4) return SPECDEC_ERR_ARG; g_p1_ctas = value; return 0; }
+  if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
+  if (!strcmp(name, "no_fused_tail")) { g_no_fused_tail = value; return 0; }
   return SPECDEC_ERR_ARG;
 }
 

@@ -334,3 +334,49 @@ def test_ngram_greedy_fast_path_and_near_ties(oracle_mod):
         _assert_same(o, r1, ngram=True)
         _assert_same(o, r2, ngram=True)
         assert torch.equal(r1.next_token, r2.next_token)
+
+
+@pytest.mark.parametrize("dtype,V,greedy", [("bf16", 32000, False), ("f32", 50257, False), ("bf16", 128256, True),
+                                            ("f16", 4099, False), ("bf16", 151936, False)])
+def test_fused_tail_equals_split_kernels_incl_ambiguous_accept_tests(oracle_mod, dtype, V, greedy):
+    """tail_fused_kernel (weights of the deciding row pair cached in shared memory, 16 CTAs per sequence) gives
+    the same outputs as exact_rows + sample_partial and the oracle -- including sequences whose accept test
+    falls inside the fast path's safety margin (u within 1e-4 of p/q), which take the in-kernel exact route."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g = 24, 4
+    case = make_case(B=B, gamma=g, V=V, dtype=dtype, sigma=0.5, seed=77, oracle=oracle_mod)
+    o0 = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
+    # put u on / next to the accept boundary for a third of the positions (before and after the first reject)
+    ua = case["u_accept"].clone()
+    ratio = torch.from_numpy(o0.p_tok / np.maximum(o0.q_tok, 1e-30)).float()
+    rng = np.random.RandomState(3)
+    for b in range(B):
+        for i in range(g):
+            k = rng.randint(6)
+            if k < 3 and 0.0 < float(ratio[b, i]) < 1.0:
+                ua[b, i] = float(ratio[b, i]) * (1.0 + (k - 1) * 1e-4)
+    case["u_accept"] = ua
+    kw = dict(greedy=greedy)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], ua, case["u_sample"], **kw)
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args, **kw)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"no_fused_tail", 1) == 0
+    try:
+        r2 = sd.fused_verify(*args, **kw)
+        torch.cuda.synchronize()
+    finally:
+        lib.specdec_set_option(b"no_fused_tail", 0)
+    _assert_same(o, r1)
+    _assert_same(o, r2)
+    for a, b_ in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.accept_mask, r2.accept_mask),
+                  (r1.packed, r2.packed), (r1.next_prob, r2.next_prob)):
+        assert torch.equal(a, b_)
+    # p_tok / q_tok are exact (== oracle bits) up to and including the deciding position in both pipelines;
+    # behind it the split pipeline may have made one more position exact, the other reports the 1e-6 fast value
+    n = r1.n_accepted.long().clamp(max=g - 1)
+    idx = torch.arange(g, device="cuda")[None, :] <= n[:, None]
+    assert torch.equal(r1.p_tok[idx], r2.p_tok[idx]) and torch.equal(r1.q_tok[idx], r2.q_tok[idx])
+    np.testing.assert_allclose(r1.p_tok.cpu().numpy(), r2.p_tok.cpu().numpy(), rtol=1e-5)
+    assert 0 < int(o.n_accepted.sum()) < B * g
