@@ -97,11 +97,19 @@ SPECDEC_API int specdec_verify(const void* target_logits, const void* draft_logi
 /* Measurement hook (bench.py): when non-NULL, specdec_verify records these cudaEvent_t on its stream
  * before the row-statistics kernel, between the two kernels and after the decide kernel. */
 SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end);
-/* Test hooks: "force_ldg"=1 makes the row kernel use vectorised LDG instead of the TMA pipeline;
- * "no_fast_nucleus"=1 / "no_fast_ngram"=1 force the exact-only kernels for top-p rows / greedy n-gram verify;
- * "no_overlap"=0 enables an optional two-stream half-batch pipelining of the verify step (default 1 = off:
- * measured no gain on B200, the step is instruction-issue bound). */
+/* Test / tuning hooks (defaults in brackets):
+ *  "force_ldg"=1 [0]        row kernel uses vectorised LDG instead of the TMA pipeline;
+ *  "no_fast_nucleus"=1 [0]  top-p rows skip nucleus_fast_kernel and nucleus_hist_kernel (exact band search only);
+ *  "no_hist_nucleus"=1 [0]  flat top-p rows skip nucleus_hist_kernel (band search instead of the histogram select);
+ *  "no_fast_ngram"=1 [0]    greedy n-gram verify takes the exact kernels;
+ *  "no_fused_tail"=1 [0]    exact_rows + sample_partial kernels instead of tail_fused_kernel;
+ *  "chunks"=n [2]           batch chunks pipelined on two streams (bf16/fp16, B >= 64 n; 1 = off; "no_overlap"=1 is
+ *                           the same as "chunks"=1);  "p1_ctas"=k [3] row-kernel CTAs per SM for chunks > 0;
+ *  "tf_ch"=k [20]           CTAs per sequence of tail_fused_kernel. */
 SPECDEC_API int specdec_set_option(const char* name, int value);
+/* Test hook: copies 16 device-side counters of nucleus_hist_kernel to out16 (host memory; synchronises):
+ * [0..6] failed attempts by reason, [7] rows left to the slow path, [8] rows resolved, [9] attempts. */
+SPECDEC_API int specdec_debug_stats(unsigned long long* out16, int reset);
 
 /* LogitsProcessor.__call__ materialised: probs[rows,V] fp32 = softmax(_process(logits)/T)
  * (utils/logits_processor.py:13-15).  row_stats (nullable) receives 8 floats per row:

@@ -367,12 +367,29 @@ __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw
     }
     if (mkeep < cntc) {  // keep the first mkeep ties in ascending index order
       int lo = 0, hi = V - 1;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        u64 c2 = 0;
-        for (int i = gp.first(); i < m; i += gp.stride()) c2 += (fkey(cz[i]) == cutkey && cj[i] <= mid) ? 1u : 0u;
-        c2 = gp.sum(c2);
-        if (c2 >= mkeep) hi = mid; else lo = mid + 1;
+      if (BLK && cntc <= (u64)blockDim.x) {
+        // tie group fits one element per thread: gather its indices (the masses in cw are no longer needed),
+        // then every bisection step is a single hardware barrier-count
+        int* tl = (int*)cw;
+        __syncthreads();
+        if (threadIdx.x == 0) gp.shu[0] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < m; i += blockDim.x)
+          if (fkey(cz[i]) == cutkey) tl[atomicAdd(&gp.shu[0], 1u)] = cj[i];
+        __syncthreads();
+        const int myj = ((u64)threadIdx.x < cntc) ? tl[threadIdx.x] : 0x7FFFFFFF;
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          if ((u64)__syncthreads_count(myj <= mid) >= mkeep) hi = mid; else lo = mid + 1;
+        }
+      } else {
+        while (lo < hi) {
+          const int mid = (lo + hi) >> 1;
+          u64 c2 = 0;
+          for (int i = gp.first(); i < m; i += gp.stride()) c2 += (fkey(cz[i]) == cutkey && cj[i] <= mid) ? 1u : 0u;
+          c2 = gp.sum(c2);
+          if (c2 >= mkeep) hi = mid; else lo = mid + 1;
+        }
       }
       jcut = lo;
     }
@@ -721,7 +738,8 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
     }
     if (threadIdx.x == 0) {
       RowOut o;
-      o.m = m; o.mc = mc; o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0; o.inv = 0.0f;
+      o.m = m; o.mc = mc; o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
+      o.inv = S1f;  // unresolved rows: the MUFU T=1 mass (relative to the max) for nucleus_hist_kernel
       if (ok) {
         o.cut = s_cut; o.jcut = s_jcut; o.Sfix = s_Sfix; o.flags = 1;
         o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(s_Sfix), 0x1p-40f));
@@ -729,6 +747,254 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
       job.out[r] = o;
     }
     __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// nucleus_hist_kernel (pure top-p, rows nucleus_fast_kernel left unresolved = flat rows whose nucleus holds
+// thousands of tokens, up to ~90 % of the vocabulary for random-init models).  The cut is located by a
+// radix-select over the VALUE axis whose cost does not depend on the size of the nucleus:
+//   level sweeps (approximate, MUFU): every thread counts its elements into a PRIVATE 256-bin byte
+//     histogram in shared memory (column tid of a [256][512] byte array: no atomics, no bank conflicts),
+//     bins uniform in (top - z); bin masses = count x mass(bin centre), with the rigorous half-bin bound
+//     as slack; the bins that are certainly kept / possibly kept bracket the cut.  The next level zooms
+//     into the bracket (256x finer) until it holds <= NH_CAP elements (1 level for 3*randn rows, 2-3 for
+//     near-uniform rows).
+//   exact sweep: canonical T=1 mass of every element (S1), exact mass / tempered weight of everything
+//     above the bracket, compaction of the bracket's elements; the cut is then selected among them by
+//     select_cut_group with exact integers.  The bracket is VERIFIED with the exact sums
+//     (G_above <= thr < G_above + M_band); a row failing any check stays unresolved and is redone by
+//     rowstats_kernel, so the histogram levels can only cost time, never change a result.
+// ---------------------------------------------------------------------------------------------
+constexpr int NH_T = 512, NH_BINS = 256, NH_CAP = 8192, NH_RV = 32, NH_SLOTS = 32;  // private candidate slots per thread (indices only)
+// failure statistics of nucleus_hist_kernel (attempts / rows): [0] inconsistent estimate, [1] byte counter wrapped,
+// [2] nucleus reaches the 2^-40 tail, [3] levels exhausted, [4] private slots overflowed, [5] bracket above the cut,
+// [6] bracket below the cut, [7] rows left to the slow path, [8] rows resolved, [9] attempts
+__device__ unsigned long long g_nh_stats[16];
+constexpr size_t NH_SMEM = (size_t)(NH_BINS + 1) * NH_T;  // 128.5 KB (256 bins + a spare); later reused for the candidates (NH_CAP * 16 B)
+
+template <int DT>
+__global__ void __launch_bounds__(NH_T, 1) nucleus_hist_kernel(RowJob job) {
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  __shared__ unsigned cnt[NH_BINS];
+  __shared__ float wsum[NH_T / 32];
+  __shared__ u64 sh64[33];
+  __shared__ float shf[33];
+  __shared__ unsigned shu[33];
+  __shared__ int s_count;
+  unsigned char* hist = dyn_smem;
+  // exact stage: [0, 64 KB) private candidate slots, later the masses cw; [64 KB, 128 KB) dense candidates
+  u64* cw = (u64*)dyn_smem;
+  float* cz = (float*)(dyn_smem + (size_t)NH_CAP * 8);
+  int* cj = (int*)(dyn_smem + (size_t)NH_CAP * 12);
+  const int V = job.V, NV = (V + 7) >> 3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float c = job.c, c1 = job.c1;
+  const float top_p = (float)((double)job.tpq * (1.0 / 4294967296.0));
+  for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+    const RowOut ro = job.out[r];
+    if (ro.flags & 1) continue;
+    const float m = ro.m, S1f = ro.inv;
+    if (!(m > -INFINITY) || !(m < INFINITY) || !(S1f > 0.0f) || !(S1f < INFINITY)) continue;  // block-uniform
+    const void* row = row_ptr<DT>(job, r);
+    const bool aligned = (((size_t)row) & 15) == 0;
+    const float mc = __fmul_rn(m, c), mc1 = __fmul_rn(m, c1);
+    const float thr_f = S1f * top_p;
+    // A failed attempt (inconsistent estimates, bracket missed the cut, too many candidates) is retried with
+    // 4x the slack and half the candidate budget before the row is left to the slow path.
+    bool done = false;
+    for (int attempt = 0; attempt < 3 && !done; ++attempt) {
+    const float slack_mul = (float)(1 << (2 * attempt));
+    const u64 focus_max = (u64)((NH_CAP / 2) >> attempt);
+    // ---- histogram levels: bracket (zb, zt] of the value axis that contains the cut ----
+    float zt = m, zb = -INFINITY;
+    float scale = (float)NH_BINS / 27.725887f;  // level 0: x = m - z in [0, 40 ln 2): masses below 2^-40 are 0
+    bool ok = false;
+    for (int level = 0; level < 5 && !ok; ++level) {
+      float fa = 0.0f;  // MUFU mass of the elements above zt
+      for (int i = tid; i < NH_BINS; i += NH_T) cnt[i] = 0;
+      for (int base = 0; base < NV; base += NH_RV * NH_T) {  // rounds of <= 256 elements per thread (byte counters)
+        uint4* h4 = (uint4*)hist;
+#pragma unroll
+        for (int q = 0; q < NH_BINS / 16; ++q) h4[q * NH_T + tid] = make_uint4(0u, 0u, 0u, 0u);  // (spare bin: never read)
+        __syncthreads();
+        const int vend = min(NV, base + NH_RV * NH_T);
+        sweep_range<DT, NH_T>(row, V, aligned, base, vend, [&](const float(&x)[8], int) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const float z = x[k];
+            if (level == 0) {
+              const int b = min(__float2int_rz(__fmul_rn(__fsub_rn(zt, z), scale)), NH_BINS - 1);
+              hist[b * NH_T + tid]++;
+            } else {  // branch-free: elements outside (zb, zt] are counted in the spare bin NH_BINS
+              const float e = ex2_approx(__fmaf_rn(z, c1, -mc1));
+              const float t = fminf(__fmul_rn(__fsub_rn(zt, z), scale), (float)NH_BINS);
+              const bool above = z > zt;
+              fa += above ? e : 0.0f;
+              hist[__float2int_rz(above ? (float)NH_BINS : t) * NH_T + tid]++;
+            }
+          }
+        });
+        __syncthreads();
+        for (int b = warp; b < NH_BINS; b += NH_T / 32) {
+          const unsigned* hr = (const unsigned*)(hist + b * NH_T);
+          unsigned sacc = 0;
+#pragma unroll
+          for (int q = 0; q < NH_T / 128; ++q) sacc = __dp4a(hr[lane + 32 * q], 0x01010101u, sacc);
+          sacc = __reduce_add_sync(0xffffffffu, sacc);
+          if (lane == 0) cnt[b] += sacc;
+        }
+        __syncthreads();
+      }
+      // mass above the range (level 0: nothing is above the row maximum)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) fa += __shfl_xor_sync(0xffffffffu, fa, o);
+      if (lane == 0) wsum[warp] = fa;
+      __syncthreads();
+      float A_above = 0.0f;
+#pragma unroll
+      for (int w = 0; w < NH_T / 32; ++w) A_above += wsum[w];
+      __syncthreads();
+      // estimated cumulative mass per bin (threads 0..255 = bins), half-bin worst case as slack
+      // Slack of the estimate (the bracket is verified exactly afterwards, so it only has to be usually right):
+      // statistical part = 4 sigma of the bin masses (cnt elements uniform over the bin, half-width `rel`),
+      // systematic part (density slope inside a bin, convexity of exp) = 25 % of the half-bin bound, + MUFU / S1f error.
+      const float rel = 0.36f * c1 / scale + 1e-6f;
+      float massb = 0.0f, varb = 0.0f;
+      unsigned myc = 0;
+      if (tid < NH_BINS) {
+        myc = cnt[tid];
+        const float zmid = zt - ((float)tid + 0.5f) / scale;
+        massb = (float)myc * ex2_approx(fminf(__fmaf_rn(zmid, c1, -mc1), 0.0f));
+        varb = myc ? (rel * massb) * (rel * massb) / (3.0f * (float)myc) : 0.0f;
+      }
+      float incl = massb, vincl = varb;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const float t = __shfl_up_sync(0xffffffffu, incl, o), t2 = __shfl_up_sync(0xffffffffu, vincl, o);
+        if (lane >= o) { incl += t; vincl += t2; }
+      }
+      if (lane == 31) { wsum[warp] = incl; shf[warp] = vincl; }
+      __syncthreads();
+      float off = 0.0f, voff = 0.0f;
+      for (int w = 0; w < warp; ++w) { off += wsum[w]; voff += shf[w]; }
+      const float cumE = off + incl, cumX = cumE - massb, varE = voff + vincl, varX = varE - varb;
+      // (never more than the half-bin worst case rel * cum: rows whose top token dominates the mass)
+      const float slE = slack_mul * fminf(rel * cumE, 5.0f * sqrtf(varE) + 0.25f * rel * cumE) + 1e-4f * (A_above + cumE);
+      const float slX = slack_mul * fminf(rel * cumX, 5.0f * sqrtf(fmaxf(varX, 0.0f)) + 0.25f * rel * cumX) + 1e-4f * (A_above + cumX);
+      const bool certain = tid < NH_BINS && (A_above + cumE + slE <= thr_f);
+      const bool possible = tid < NH_BINS && (A_above + cumX - slX <= thr_f);
+      const int nc = __syncthreads_count(certain), np = __syncthreads_count(possible);
+      u64 tot_c = block_sum_u64((u64)myc, sh64);
+      if (nc >= NH_BINS || np < 1) { if (tid == 0) atomicAdd(&g_nh_stats[0], 1ull); break; }  // inconsistent estimates
+      if (level == 0 && tot_c != (u64)NV * 8ull) { if (tid == 0) atomicAdd(&g_nh_stats[1], 1ull); break; }  // a byte counter wrapped (giant tie group)
+      const int b_lo = max(nc - 1, 0), b_hi = max(np - 1, b_lo);
+      if (level == 0 && b_hi == NH_BINS - 1) { if (tid == 0) atomicAdd(&g_nh_stats[2], 1ull); break; }  // nucleus reaches the 2^-40 tail
+      const u64 n_focus = block_sum_u64((tid >= b_lo && tid <= b_hi && tid < NH_BINS) ? (u64)myc : 0ull, sh64);
+      const float nzt = (b_lo > 0) ? zt - (float)b_lo / scale : zt;
+      const float nzb = zt - (float)(b_hi + 1) / scale;
+      if (!(nzb < nzt)) break;
+      zt = nzt; zb = nzb;
+      scale = (float)NH_BINS / (zt - zb);
+      if (n_focus <= focus_max) ok = n_focus > 0;  // first attempt: average 8 of the 32 private slots per thread
+      else if (!(scale < 1e30f)) break;
+    }
+    if (tid == 0) atomicAdd(&g_nh_stats[9], 1ull);
+    if (!ok) { if (tid == 0) atomicAdd(&g_nh_stats[3], 1ull); continue; }  // block-uniform
+    // ---- exact sweep: S1, mass / tempered weight above the bracket, candidates (zb, zt] ----
+    // Candidate indices go to PRIVATE slots (slot-major [NH_SLOTS][512] ints: no votes, scans or atomics in
+    // the sweep); they are made dense afterwards (values re-read through L2).  A thread with more than
+    // NH_SLOTS hits leaves the row to the slow path.
+    const float th = nextafterf(zb, INFINITY), up = nextafterf(zt, INFINITY);  // (zb, zt] == [th, up), th > -inf
+    int* stg = (int*)dyn_smem;
+    int pc = 0;
+    u64 S1l = 0, Gl = 0, STl = 0;
+    const bool tempered = (c != c1);
+    const float2 c12 = make_float2(c1, c1), nmc12 = make_float2(-mc1, -mc1), cT2 = make_float2(c, c), nmcT2 = make_float2(-mc, -mc);
+    __syncthreads();
+    for (int base = (tid >> 5) << 5; base < NV; base += 2 * NH_T) {  // warp-uniform
+      float x0[8], x1[8];
+      const int v0 = base + lane, v1 = v0 + NH_T;
+      load8<DT>(row, min(v0, NV - 1), V, aligned, x0);
+      load8<DT>(row, min(v1, NV - 1), V, aligned, x1);
+      auto emit = [&](float(&x)[8], int v) {
+        if (v >= NV) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) x[k] = -INFINITY;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 z2 = make_float2(x[2 * k], x[2 * k + 1]);
+          const float2 e = cweight2(z2, c12, nmc12);
+          const u64 w0 = fix40(e.x), w1 = fix40(e.y);
+          S1l += w0 + w1;
+          const bool a0 = z2.x >= up, a1 = z2.y >= up;
+          if (a0) Gl += w0;
+          if (a1) Gl += w1;
+          if (tempered) {
+            const float2 et = cweight2(z2, cT2, nmcT2);
+            if (a0) STl += fix40(et.x);
+            if (a1) STl += fix40(et.y);
+          }
+          if (!a0 && z2.x >= th) {  // (-inf padding never qualifies)
+            if (pc < NH_SLOTS) stg[pc * NH_T + tid] = v * 8 + 2 * k;
+            ++pc;
+          }
+          if (!a1 && z2.y >= th) {
+            if (pc < NH_SLOTS) stg[pc * NH_T + tid] = v * 8 + 2 * k + 1;
+            ++pc;
+          }
+        }
+      };
+      emit(x0, v0);
+      if (base + NH_T < NV) emit(x1, v1);  // warp-uniform
+    }
+    // dense candidate list: block exclusive scan of the per-thread counts, then each thread moves its entries
+    int incl_pc = pc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl_pc, o);
+      if (lane >= o) incl_pc += t;
+    }
+    __syncthreads();
+    if (lane == 31) shu[warp] = (unsigned)incl_pc;
+    const int over = __syncthreads_count(pc > NH_SLOTS);
+    int off_pc = incl_pc - pc, n = 0;
+    for (int w = 0; w < NH_T / 32; ++w) { const int t = (int)shu[w]; if (w < warp) off_pc += t; n += t; }
+    if (!over && n <= NH_CAP) {
+      float* czd = (float*)(dyn_smem + (size_t)NH_CAP * 8);
+      int* cjd = (int*)(dyn_smem + (size_t)NH_CAP * 12);
+      for (int i = 0; i < pc; ++i) {
+        const int j = stg[i * NH_T + tid];
+        czd[off_pc + i] = load1<DT>(row, j);
+        cjd[off_pc + i] = j;
+      }
+    }
+    __syncthreads();
+    const u64 S1 = block_sum_u64(S1l, sh64), G_above = block_sum_u64(Gl, sh64);
+    const u64 S_above = tempered ? block_sum_u64(STl, sh64) : G_above;
+    if (over || n <= 0 || n > NH_CAP) { if (tid == 0) atomicAdd(&g_nh_stats[4], 1ull); continue; }
+    const u64 thr = scale_q32(S1, job.tpq);
+    u64 mb = 0;
+    for (int i = tid; i < n; i += NH_T) mb += fix40(cweight(cz[i], c1, mc1));
+    const u64 M_band = block_sum_u64(mb, sh64);
+    if (G_above > thr || G_above + M_band <= thr) {  // bracket missed the cut: retry wider
+      if (tid == 0) atomicAdd(&g_nh_stats[G_above > thr ? 5 : 6], 1ull);
+      continue;
+    }
+    float cut; int jcut; u64 Sfix;
+    const Grp<true> gp{sh64, shu};
+    select_cut_group<true>(gp, cz, cj, cw, n, V, 0, 1, job.tpq, S1, G_above, S_above, c, mc, c1, mc1, cut, jcut, Sfix);
+    if (tid == 0) {
+      RowOut o;
+      o.m = m; o.mc = mc;
+      o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(Sfix), 0x1p-40f));
+      o.cut = cut; o.jcut = jcut; o.flags = 1; o.Sfix = Sfix;
+      job.out[r] = o;
+    }
+    done = true;
+    __syncthreads();
+    }  // attempt
+    if (tid == 0) atomicAdd(&g_nh_stats[done ? 8 : 7], 1ull);
   }
 }
 
@@ -1163,6 +1429,7 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
 static int g_no_fast_ngram = 0;    // test hook: specdec_set_option("no_fast_ngram", 1)
 static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
+static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 static int g_sms = 0;
@@ -1217,6 +1484,12 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
       cudaError_t e = cudaFuncSetAttribute(nucleus_fast_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
       nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj);
+      if (!g_no_hist_nucleus) {  // flat rows: radix-select by private histograms, cost independent of the nucleus size
+        cudaError_t e3 = cudaFuncSetAttribute(nucleus_hist_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NH_SMEM);
+        if (e3 != cudaSuccess) return e3;
+        const int gh = (int)(rj.R < (long long)num_sms() ? rj.R : (long long)num_sms());
+        nucleus_hist_kernel<DT><<<gh, NH_T, NH_SMEM, st>>>(rj);
+      }
       RowJob rj2 = rj;
       rj2.skip_resolved = 1;
       {
@@ -1541,9 +1814,21 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "p1_ctas")) { if (value < 1 || value > 4) return SPECDEC_ERR_ARG; g_p1_ctas = value; return 0; }
   if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
+  if (!strcmp(name, "no_hist_nucleus")) { g_no_hist_nucleus = value; return 0; }
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
   if (!strcmp(name, "no_fused_tail")) { g_no_fused_tail = value; return 0; }
   return SPECDEC_ERR_ARG;
+}
+
+int specdec_debug_stats(unsigned long long* out16, int reset) {
+  if (!out16) return SPECDEC_ERR_ARG;
+  cudaError_t e = cudaMemcpyFromSymbol(out16, g_nh_stats, sizeof(unsigned long long) * 16);
+  if (e != cudaSuccess) return (int)e;
+  if (reset) {
+    unsigned long long z[16] = {0};
+    e = cudaMemcpyToSymbol(g_nh_stats, z, sizeof(z));
+  }
+  return (int)e;
 }
 
 int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {

@@ -380,3 +380,61 @@ def test_fused_tail_equals_split_kernels_incl_ambiguous_accept_tests(oracle_mod,
     assert torch.equal(r1.p_tok[idx], r2.p_tok[idx]) and torch.equal(r1.q_tok[idx], r2.q_tok[idx])
     np.testing.assert_allclose(r1.p_tok.cpu().numpy(), r2.p_tok.cpu().numpy(), rtol=1e-5)
     assert 0 < int(o.n_accepted.sum()) < B * g
+
+
+@pytest.mark.parametrize("dtype", ["bf16", "f32", "f16"])
+@pytest.mark.parametrize("scale,V", [(3.0, 128256), (1.0, 128256), (0.3, 128256), (0.02, 128256), (1.0, 50257), (0.5, 151936)])
+def test_histogram_nucleus_on_flat_rows(oracle_mod, dtype, scale, V):
+    """flat rows (random-init models: the nucleus holds thousands of tokens up to ~90 % of the vocabulary) go
+    through nucleus_hist_kernel (radix-select over the value axis by private histograms + one exact sweep);
+    the kept sets / probabilities equal the band-search path bit for bit and the verify equals the oracle."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g = 3, 2
+    case = make_case(B=B, gamma=g, V=V, dtype=dtype, sigma=0.3 * scale, seed=int(scale * 100) + V % 13, scale=scale)
+    gen = torch.Generator().manual_seed(11)
+    for mode in ("nucleus0.9", "nucleus0.9_t0.7"):
+        m = MODES[mode]
+        tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(B * g, V),
+                                        torch.rand(B * g, generator=gen).numpy(), **m)
+        case["draft_tokens"] = torch.from_numpy(tok.reshape(B, g))
+        args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+        r1 = sd.fused_verify(*args, **m)
+        p1, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+        assert lib.specdec_set_option(b"no_hist_nucleus", 1) == 0
+        try:
+            r2 = sd.fused_verify(*args, **m)
+            p2, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+        finally:
+            lib.specdec_set_option(b"no_hist_nucleus", 0)
+        assert torch.equal(p1, p2), "kept set / probabilities differ from the band-search path"
+        assert torch.equal(r1.n_accepted, r2.n_accepted) and torch.equal(r1.next_token, r2.next_token)
+        assert torch.equal(r1.p_tok, r2.p_tok) and torch.equal(r1.q_tok, r2.q_tok)
+        kept = (p1 > 0).sum(-1)
+        assert int(kept.min()) > 1000  # genuinely large nuclei
+        o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
+        _assert_same(o, r1)
+
+
+def test_histogram_nucleus_resolves_flat_rows_without_fallback():
+    """perf guard: on synthetic flat rows every row is resolved by nucleus_fast / nucleus_hist on the first
+    attempt (a row left to the band-search slow path costs ~100x; results would still be exact)."""
+    import ctypes
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    st = (ctypes.c_ulonglong * 16)()
+    assert lib.specdec_debug_stats(ctypes.cast(st, ctypes.c_void_p), 1) == 0
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    B, g, V = 32, 4, 128256
+    for scale in (3.0, 0.5, 0.02):
+        t = (scale * torch.randn(B, g + 1, V, device="cuda", generator=gen)).to(torch.bfloat16)
+        d = (t[:, :g].float() + 0.2 * scale * torch.randn(B, g, V, device="cuda", generator=gen)).to(torch.bfloat16)
+        toks = torch.randint(V, (B, g), device="cuda", generator=gen)
+        sd.fused_verify(t, d, toks, torch.rand(B, g, device="cuda", generator=gen),
+                        torch.rand(B, device="cuda", generator=gen), top_p=0.9)
+    torch.cuda.synchronize()
+    assert lib.specdec_debug_stats(ctypes.cast(st, ctypes.c_void_p), 1) == 0
+    s = list(st)
+    assert s[8] == 3 * B * (2 * g + 1), s      # every row resolved by the histogram kernel
+    assert s[7] == 0, s                        # nothing left to the slow path
+    assert sum(s[0:7]) <= 0.05 * s[8], s       # retried attempts (wider slack) stay rare
