@@ -1810,7 +1810,7 @@ int specdec_set_option(const char* name, int value) {
   if (!name) return SPECDEC_ERR_ARG;
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
   if (!strcmp(name, "no_overlap")) { g_chunks = value ? 1 : 2; return 0; }
-  if (!strcmp(name, "chunks")) { if (value < 1 || value > 8) return SPECDEC_ERR_ARG; g_chunks = value; return 0; }
+  if (!strcmp(name, "chunks")) { if (value < 0 || value > 8) return SPECDEC_ERR_ARG; g_chunks = value ? value : 2; return 0; }  // 0 = default
   if (!strcmp(name, "p1_ctas")) { if (value < 1 || value > 4) return SPECDEC_ERR_ARG; g_p1_ctas = value; return 0; }
   if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
