@@ -1669,6 +1669,11 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   int C = g_chunks;
   if (masked || dj.gamma == 0 || B < 64 * C || C > 8 || DT == DT_F32) C = 1;  // (fp32 rows: LDG row kernel, no gain)
   if (C > 1 && !g_aux_stream) {
+    // (streams / events cannot be created while the caller's stream is being captured into a CUDA graph)
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) C = 1;
+  }
+  if (C > 1 && !g_aux_stream) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
     if ((e = cudaStreamCreateWithPriority(&g_aux_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;

@@ -438,3 +438,32 @@ def test_histogram_nucleus_resolves_flat_rows_without_fallback():
     assert s[8] == 3 * B * (2 * g + 1), s      # every row resolved by the histogram kernel
     assert s[7] == 0, s                        # nothing left to the slow path
     assert sum(s[0:7]) <= 0.05 * s[8], s       # retried attempts (wider slack) stay rare
+
+
+@pytest.mark.parametrize("B", [8, 160])
+def test_verify_step_is_cuda_graph_capturable(oracle_mod, B):
+    """the whole verify step (memset, row kernel(s), plan, fused tail; for B >= 128 bf16 the two-chunk fork/join
+    on the library's auxiliary stream) can be captured into a CUDA graph and replayed on new logits."""
+    import specdec_b200 as sd
+    V, g = 32000, 3
+    c1 = make_case(B=B, gamma=g, V=V, dtype="bf16", sigma=0.5, seed=61, oracle=oracle_mod)
+    c2 = make_case(B=B, gamma=g, V=V, dtype="bf16", sigma=0.8, seed=62, oracle=oracle_mod)
+    keys = ("target", "draft", "draft_tokens", "u_accept", "u_sample")
+    static = [c1[k].cuda().clone() for k in keys]
+    sd.fused_verify(*static)  # eager warm-up (creates the library's stream / events, sizes the workspace)
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        sd.fused_verify(*static)
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        r = sd.fused_verify(*static)
+    for case in (c2, c1):
+        for dst, k in zip(static, keys):
+            dst.copy_(case[k].cuda())
+        graph.replay()
+        torch.cuda.synchronize()
+        o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
+        _assert_same(o, r)
