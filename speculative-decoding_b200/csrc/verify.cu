@@ -790,6 +790,9 @@ __global__ void __launch_bounds__(NH_T, 1) nucleus_hist_kernel(RowJob job) {
   const int V = job.V, NV = (V + 7) >> 3, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float c = job.c, c1 = job.c1;
   const float top_p = (float)((double)job.tpq * (1.0 / 4294967296.0));
+  // byte column of this thread inside a 512-byte bin row: the 32 lanes of a warp hit 32 different 4-byte words
+  // (byte stores of four lanes into one word would be serialised)
+  const int hcol = (tid & 127) * 4 + (tid >> 7);
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
     const RowOut ro = job.out[r];
     if (ro.flags & 1) continue;
@@ -824,13 +827,13 @@ __global__ void __launch_bounds__(NH_T, 1) nucleus_hist_kernel(RowJob job) {
             const float z = x[k];
             if (level == 0) {
               const int b = min(__float2int_rz(__fmul_rn(__fsub_rn(zt, z), scale)), NH_BINS - 1);
-              hist[b * NH_T + tid]++;
+              hist[b * NH_T + hcol]++;
             } else {  // branch-free: elements outside (zb, zt] are counted in the spare bin NH_BINS
               const float e = ex2_approx(__fmaf_rn(z, c1, -mc1));
               const float t = fminf(__fmul_rn(__fsub_rn(zt, z), scale), (float)NH_BINS);
               const bool above = z > zt;
               fa += above ? e : 0.0f;
-              hist[__float2int_rz(above ? (float)NH_BINS : t) * NH_T + tid]++;
+              hist[__float2int_rz(above ? (float)NH_BINS : t) * NH_T + hcol]++;
             }
           }
         });
