@@ -697,10 +697,22 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
     qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));
     qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
     const float th = block_min_f(qm, shf);
+    // Flat rows cannot be resolved here (their nucleus holds thousands of tokens): if the 512 per-thread maxima --
+    // roughly the 512 largest logits -- carry less than 3/4 of the mass the nucleus needs, sweep 2 is skipped and
+    // the row goes to nucleus_hist_kernel.  (A heuristic: it only decides which exact kernel does the row.)
+    float wt = (tm > -INFINITY) ? ex2_approx(__fmul_rn(__fsub_rn(tm, m), c1)) : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+    if (lane == 0) shf[threadIdx.x >> 5] = wt;
+    __syncthreads();
+    float Wt = 0.0f;
+#pragma unroll
+    for (int w = 0; w < RS_NT / 32; ++w) Wt += shf[w];
+    const bool flat = Wt < 0.75f * (float)((double)job.tpq * (1.0 / 4294967296.0)) * S1f;  // block-uniform
     // sweep 2: compaction of the candidates (warp-aggregated, vote-gated)
     if (threadIdx.x == 0) s_count = 0;
     __syncthreads();
-    for (int base = (threadIdx.x >> 5) << 5; base < NV; base += 4 * RS_NT) {
+    for (int base = (threadIdx.x >> 5) << 5; base < NV && !flat; base += 4 * RS_NT) {
       float x[4][8];
       int vv[4];
 #pragma unroll
