@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libspecdec_b200.so")
+LIB_PATH = os.environ.get("SPECDEC_B200_LIB") or os.path.join(_HERE, "libspecdec_b200.so")  # (override: tuning builds)
 
 F32, BF16, F16 = 0, 1, 2
 SAMPLE_GREEDY, SAMPLE_INVCDF = 0, 1

@@ -1,21 +1,18 @@
 // hybrid.cuh -- the production verify pipeline (included by verify.cu inside namespace specdec).
 //
-// The canonical (oracle-reproducible) arithmetic costs ~16 issue slots per logit because exp2 is a
-// polynomial on the FMA pipe.  Only a few rows per sequence actually need it, so the step is split
-// into three launches whose tails are chained with "last CTA done" counters (no host sync, no spin):
+// The canonical (oracle-reproducible) arithmetic costs ~12 issue slots per logit because exp2 is a
+// polynomial on the FMA pipe.  Only a few rows per sequence actually need it, so the step is split:
 //
 //   1. rowfast_tma_kernel / rowfast_kernel: every row, ONE pass over HBM: online max + sum of MUFU
 //      ex2 (5 slots/logit).  The row max is exact; the sum is good to ~1e-6 relative.
-//      Tail (CTA that completes a sequence's last row) = plan: p~/q~ of the draft tokens from the
-//      fast sums and the accept test with a 1e-3 relative safety margin => sure-accept /
-//      sure-reject / ambiguous.  Rows that decide something (ambiguous positions + the first sure
-//      reject, whose residual needs exact normalisers) become tasks.
-//   2. exact_rows_kernel: canonical sum of the task rows (u64 atomics: order independent).
-//      Tail (last CTA of a sequence's tasks) = decide: final decisions from exact sums where they
-//      exist (identical to the oracle's because fast ones are only trusted outside the margin).
-//   3. sample_partial_kernel: the one sweep the next token needs -- residual max(0,p-q) or the
-//      bonus/target row -- as per-256-element integer partial sums, CH CTAs per sequence.
-//      Tail (last of the CH CTAs) = finalize: scan of the partials, inverse-CDF location, outputs.
+//   2. plan_kernel (one warp per sequence): p~/q~ of the draft tokens from the fast sums and the accept
+//      test with a 1e-3 relative safety margin => sure-accept / sure-reject / ambiguous.  Sequences
+//      without ambiguous positions are decided on the spot.
+//   3. tail_fused_kernel (tail_fused.cuh, default): exact normalisers of the deciding row pair, residual
+//      partial sums from the weights cached in shared memory, token location -- one launch.
+//   3'/4'. exact_rows_kernel + sample_partial_kernel: the same work as two launches without the cache
+//      (fallback for huge vocabularies, test hook "no_fused_tail"; sample_partial also serves the masked
+//      modes).  Tails are chained with "last CTA done" counters (no host sync, no spin).
 //
 // top-k / nucleus modes use the exact rowstats_kernel for every row (their kept sets need exact
 // masses) followed by plan_kernel (no tasks).  Outputs are bit-identical to the exact-everywhere path.

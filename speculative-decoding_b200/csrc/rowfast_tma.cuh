@@ -1,9 +1,10 @@
 // rowfast_tma.cuh -- the HBM-bound row-statistics kernel as a TMA bulk-copy pipeline (included inside
 // namespace specdec by hybrid.cuh).
 //
-// Persistent CTAs (3 per SM): one producer warp streams each logit row HBM -> shared memory with
-// cp.async.bulk (1-D TMA, SASS UBLKCP) into an 8-stage x 8 KB ring, completion signalled through
-// mbarrier transaction counts; 8 consumer warps read the stages with conflict-free 16-byte LDS and
+// Persistent CTAs (4 per SM): one producer warp streams each logit row HBM -> shared memory with
+// cp.async.bulk (1-D TMA, SASS UBLKCP) into a 3-stage x 16 KB ring per CTA (4 CTAs / SM), completion signalled through
+// mbarrier transaction counts; 8 consumer warps read the stages with conflict-free 16-byte LDS (4 vectors per
+// thread and stage: measured 0.1044 ms vs 0.1095 ms with 6 x 8 KB stages -- fewer barrier round trips) and
 // keep the online (max, sum of MUFU ex2) per thread.  ~190 KB of loads are in flight per SM
 // independent of what the consumers are doing (block reductions, row epilogues), which is what the
 // plain LDG version (rowfast_kernel) could not sustain.  Used when every row is 16-byte aligned and a
@@ -12,8 +13,14 @@
 
 constexpr int TS_CONSUMERS = 256;
 constexpr int TS_THREADS = TS_CONSUMERS + 32;
-constexpr int TS_STAGES = 6;
-constexpr int TS_STAGE_BYTES = 8192;
+#ifndef TS_STAGES_V
+#define TS_STAGES_V 3
+#endif
+#ifndef TS_STAGE_BYTES_V
+#define TS_STAGE_BYTES_V 16384
+#endif
+constexpr int TS_STAGES = TS_STAGES_V;
+constexpr int TS_STAGE_BYTES = TS_STAGE_BYTES_V;
 constexpr int TS_SMEM = TS_STAGES * TS_STAGE_BYTES;
 
 __device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
@@ -136,12 +143,14 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
       const unsigned off = (unsigned)k * TS_STAGE_BYTES;
       const int nvec = (int)(min((unsigned)TS_STAGE_BYTES, row_bytes - off) >> 4);
       const uint4* sp = reinterpret_cast<const uint4*>(ring + stage * TS_STAGE_BYTES);
-      uint4 a, b;
-      const bool ha = tid < nvec, hb = tid + TS_CONSUMERS < nvec;
-      if (ha) a = sp[tid];
-      if (hb) b = sp[tid + TS_CONSUMERS];
-      if (ha) online16<DT>(a, m, s, c);
-      if (hb) online16<DT>(b, m, s, c);
+      constexpr int VPT = TS_STAGE_BYTES / 16 / TS_CONSUMERS;  // 16-byte vectors per consumer thread and stage
+      uint4 a[VPT];
+#pragma unroll
+      for (int q = 0; q < VPT; ++q)
+        if (tid + q * TS_CONSUMERS < nvec) a[q] = sp[tid + q * TS_CONSUMERS];
+#pragma unroll
+      for (int q = 0; q < VPT; ++q)
+        if (tid + q * TS_CONSUMERS < nvec) online16<DT>(a[q], m, s, c);
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }

@@ -1568,6 +1568,7 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
 }
 
 static int g_chunks = 2;    // batch chunks pipelined on two streams (specdec_set_option("chunks", n); 1 = off)
+static int g_chunk0_pct = 50;  // share of the batch in chunk 0 when chunks == 2
 static int g_p1_ctas = 3;   // row-kernel CTAs per SM while a tail kernel of the previous chunk shares the SMs
 static int g_tf_ch = TF_CH_DEFAULT;  // CTAs per sequence of tail_fused_kernel
 static cudaStream_t g_aux_stream = nullptr;
@@ -1595,7 +1596,13 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
       if (e != cudaSuccess) return e;
       attr_set[DT] = true;
     }
-    const long long cap = (long long)(ctas_per_sm + 1) * num_sms();
+    static int occ[3] = {0, 0, 0};  // resident CTAs per SM of the persistent grid
+    if (!occ[DT]) {
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[DT], rowfast_tma_kernel<DT>, TS_THREADS, TS_SMEM) != cudaSuccess || occ[DT] < 1)
+        occ[DT] = 1;
+    }
+    const int per_sm = (ctas_per_sm + 1) < occ[DT] ? (ctas_per_sm + 1) : occ[DT];
+    const long long cap = (long long)per_sm * num_sms();
     rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   } else {
     rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
@@ -1703,7 +1710,11 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
     if ((e = launch_phase_b<DT>(dj, ws, B, st)) != cudaSuccess) return e;
   } else {
     for (int i = 0; i < C; ++i) {
-      const int b0 = (int)((long long)B * i / C), b1 = (int)((long long)B * (i + 1) / C);
+      int b0 = (int)((long long)B * i / C), b1 = (int)((long long)B * (i + 1) / C);
+      if (C == 2) {  // unequal halves: the exposed tail is the one of the last chunk
+        const int cut = (int)((long long)B * g_chunk0_pct / 100);
+        b0 = i ? cut : 0; b1 = i ? B : cut;
+      }
       DecideJob d;
       HybridWs w;
       sub_job<DT>(dj, ws, b0, b1 - b0, i, d, w);
@@ -1831,6 +1842,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
   if (!strcmp(name, "no_overlap")) { g_chunks = value ? 1 : 2; return 0; }
   if (!strcmp(name, "chunks")) { if (value < 0 || value > 8) return SPECDEC_ERR_ARG; g_chunks = value ? value : 2; return 0; }  // 0 = default
+  if (!strcmp(name, "chunk0_pct")) { if (value < 10 || value > 90) return SPECDEC_ERR_ARG; g_chunk0_pct = value; return 0; }
   if (!strcmp(name, "p1_ctas")) { if (value < 1 || value > 4) return SPECDEC_ERR_ARG; g_p1_ctas = value; return 0; }
   if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
