@@ -101,6 +101,8 @@ SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* e
  *  "force_ldg"=1 [0]        row kernel uses vectorised LDG instead of the TMA pipeline;
  *  "no_fast_nucleus"=1 [0]  top-p rows skip nucleus_fast_kernel and nucleus_hist_kernel (exact band search only);
  *  "no_hist_nucleus"=1 [0]  flat top-p rows skip nucleus_hist_kernel (band search instead of the histogram select);
+ *  "no_tma_nucleus"=0 [1]   top-p rows: first sweep of nucleus_fast_kernel as a launch of the TMA row pipeline (off by
+ *                           default: faster on flat rows, slower on LLM-like rows);
  *  "no_fast_ngram"=1 [0]    greedy n-gram verify takes the exact kernels;
  *  "no_fused_tail"=1 [0]    exact_rows + sample_partial kernels instead of tail_fused_kernel;
  *  "chunks"=n [2]           batch chunks pipelined on two streams (bf16/fp16, B >= 64 n; 1 = off; "no_overlap"=1 is

@@ -97,12 +97,16 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
   }
 }
 
-template <int DT>
+// NUC = true: pre-pass of the top-p rows (launch_rowstats): the caller passes c = log2(e) (T = 1 masses) and the row
+// epilogue additionally emits what nucleus_fast_kernel needs to go straight to its candidate sweep -- RowOut.inv =
+// the MUFU mass S (not 1/S), RowOut.cut = candidate threshold (min over the 4-lane-group maxima of the 256 consumer
+// threads: >= 64 elements lie above it), RowOut.Sfix = bits of the mass carried by the 256 per-thread maxima.
+template <int DT, bool NUC = false>
 __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
   const RowJob& job = dj.rj;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
-  __shared__ float sh_m[2][8], sh_s[2][8];
+  __shared__ float sh_m[2][8], sh_s[2][8], sh_q[2][8], sh_w[2][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
   const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
@@ -158,10 +162,20 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
     // row epilogue among the 256 consumer threads (named barrier 1; the producer keeps prefetching).
     // Scratch is double-buffered by row parity, so one barrier per row suffices.
     float wm = warp_max_f(m);
-    s = (m > -INFINITY) ? __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, wm), c))) : 0.0f;
+    const float resc = (m > -INFINITY) ? ex2_approx(__fmul_rn(__fsub_rn(m, wm), c)) : 0.0f;  // weight of my maximum
+    s = __fmul_rn(s, resc);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { sh_m[par][warp] = wm; sh_s[par][warp] = s; }
+    if (NUC) {
+      float qm = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));  // 4-lane groups: 64 groups of ~V/64 elements,
+      qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));      // the same statistics as nucleus_fast_kernel's own sweep
+      const float wq = warp_min_f(qm);
+      float wt = resc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
+      if (lane == 0) { sh_q[par][warp] = wq; sh_w[par][warp] = wt; }
+    }
     asm volatile("bar.sync 1, %0;" ::"n"(TS_CONSUMERS) : "memory");
     if (warp == 0) {
       if (lane == 0) {
@@ -175,6 +189,15 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
         RowOut o;
         o.m = M; o.mc = __fmul_rn(M, c); o.inv = __fdiv_rn(1.0f, S);
         o.cut = -INFINITY; o.jcut = job.V; o.flags = 0; o.Sfix = 0;
+        if (NUC) {
+          float th = sh_q[par][0], Wt = 0.0f;
+#pragma unroll
+          for (int w = 0; w < TS_CONSUMERS / 32; ++w) {
+            th = fminf(th, sh_q[par][w]);
+            Wt += (sh_m[par][w] > -INFINITY) ? __fmul_rn(sh_w[par][w], ex2_approx(__fmul_rn(__fsub_rn(sh_m[par][w], M), c))) : 0.0f;
+          }
+          o.inv = S; o.cut = th; o.Sfix = (u64)__float_as_uint(Wt);
+        }
         job.out[r] = o;
       }
     }

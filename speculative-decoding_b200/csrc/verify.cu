@@ -43,6 +43,7 @@ struct RowJob {
   long long R;
   RowOut* out;
   int skip_resolved;  // rowstats_kernel: skip rows whose RowOut is already flagged exact
+  int pre_stats;      // nucleus_fast_kernel: max / MUFU mass / candidate threshold come from rowfast_tma_kernel<DT, true>
 };
 
 template <int DT>
@@ -672,42 +673,47 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
     const void* row = row_ptr<DT>(job, r);
     const bool aligned = (((size_t)row) & 15) == 0;
-    // sweep 1: exact max, per-thread maxima, online MUFU sum at T = 1
-    float tm = -INFINITY, ts = 0.0f;
-    sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
-      const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
-      if (vm > tm) { ts = __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, vm), c1))); tm = vm; }
-      const float mcl = __fmul_rn(tm, c1);
+    float m, S1f, th, Wt;
+    if (job.pre_stats) {  // block-uniform: everything sweep 1 produces was emitted by rowfast_tma_kernel<DT, true>
+      const RowOut pre = job.out[r];
+      m = pre.m; S1f = pre.inv; th = pre.cut; Wt = __uint_as_float((unsigned)pre.Sfix);
+      __syncthreads();  // every thread has read the record before thread 0 overwrites it below
+    } else {
+      // sweep 1: exact max, per-thread maxima, online MUFU sum at T = 1
+      float tm = -INFINITY, ts = 0.0f;
+      sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
+        const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
+        if (vm > tm) { ts = __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, vm), c1))); tm = vm; }
+        const float mcl = __fmul_rn(tm, c1);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) ts = __fadd_rn(ts, ex2_approx(__fmaf_rn(x[k], c1, -mcl)));
-    });
-    const float m = block_max_f(tm, shf);
+        for (int k = 0; k < 8; ++k) ts = __fadd_rn(ts, ex2_approx(__fmaf_rn(x[k], c1, -mcl)));
+      });
+      m = block_max_f(tm, shf);
+      const float resc = (tm > -INFINITY) ? ex2_approx(__fmul_rn(__fsub_rn(tm, m), c1)) : 0.0f;  // weight of my maximum
+      ts = __fmul_rn(ts, resc);
+      float wt = resc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        ts += __shfl_xor_sync(0xffffffffu, ts, o);
+        wt += __shfl_xor_sync(0xffffffffu, wt, o);
+      }
+      if (lane == 0) { shf[threadIdx.x >> 5] = ts; shf[16 + (threadIdx.x >> 5)] = wt; }
+      __syncthreads();
+      S1f = 0.0f; Wt = 0.0f;
+#pragma unroll
+      for (int w = 0; w < RS_NT / 32; ++w) { S1f += shf[w]; Wt += shf[16 + w]; }
+      __syncthreads();
+      // candidate threshold: min over the 8-lane-group maxima (>= RS_NT/8 elements above it)
+      float qm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
+      qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));
+      qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
+      th = block_min_f(qm, shf);
+    }
     const float mc = __fmul_rn(m, c), mc1 = __fmul_rn(m, c1);
-    ts = (tm > -INFINITY) ? __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, m), c1))) : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ts += __shfl_xor_sync(0xffffffffu, ts, o);
-    if (lane == 0) shf[threadIdx.x >> 5] = ts;
-    __syncthreads();
-    float S1f = 0.0f;
-#pragma unroll
-    for (int w = 0; w < RS_NT / 32; ++w) S1f += shf[w];
-    __syncthreads();
-    // candidate threshold: min over the 8-lane-group maxima (>= RS_NT/8 elements above it)
-    float qm = fmaxf(tm, __shfl_xor_sync(0xffffffffu, tm, 1));
-    qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));
-    qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 4));
-    const float th = block_min_f(qm, shf);
-    // Flat rows cannot be resolved here (their nucleus holds thousands of tokens): if the 512 per-thread maxima --
-    // roughly the 512 largest logits -- carry less than 3/4 of the mass the nucleus needs, sweep 2 is skipped and
-    // the row goes to nucleus_hist_kernel.  (A heuristic: it only decides which exact kernel does the row.)
-    float wt = (tm > -INFINITY) ? ex2_approx(__fmul_rn(__fsub_rn(tm, m), c1)) : 0.0f;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) wt += __shfl_xor_sync(0xffffffffu, wt, o);
-    if (lane == 0) shf[threadIdx.x >> 5] = wt;
-    __syncthreads();
-    float Wt = 0.0f;
-#pragma unroll
-    for (int w = 0; w < RS_NT / 32; ++w) Wt += shf[w];
+    // Flat rows cannot be resolved here (their nucleus holds thousands of tokens): if the per-thread maxima --
+    // roughly the 512 (256 with the TMA pre-pass) largest logits -- carry less than 3/4 of the mass the nucleus
+    // needs, sweep 2 is skipped and the row goes to nucleus_hist_kernel.  (A heuristic: it only decides which
+    // exact kernel does the row.)
     const bool flat = Wt < 0.75f * (float)((double)job.tpq * (1.0 / 4294967296.0)) * S1f;  // block-uniform
     // sweep 2: compaction of the candidates (warp-aggregated, vote-gated)
     if (threadIdx.x == 0) s_count = 0;
@@ -1444,6 +1450,9 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
 static int g_no_fast_ngram = 0;    // test hook: specdec_set_option("no_fast_ngram", 1)
 static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
+static int g_no_tma_nucleus = 1;   // specdec_set_option("no_tma_nucleus", 0) => first sweep of the top-p rows as a TMA row-kernel launch
+                                   // (off: measured 1.42 -> 1.38 ms on flat rows but 0.55 -> 0.60 ms on LLM-like rows, whose
+                                   // second sweep then comes from HBM instead of L2)
 static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
@@ -1473,8 +1482,14 @@ static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long t
   rj.R = R;
   rj.out = (RowOut*)workspace;
   rj.skip_resolved = 0;
+  rj.pre_stats = 0;
   return 0;
 }
+
+// Top-p rows: the first sweep of nucleus_fast_kernel (row max, MUFU T=1 mass, candidate threshold) as a launch of the
+// TMA row pipeline (hybrid.cuh / rowfast_tma.cuh).  Returns false when the rows are not TMA-eligible.
+template <int DT>
+static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st);
 
 template <int DT>
 static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
@@ -1498,7 +1513,9 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
     if (!g_no_fast_nucleus) {
       cudaError_t e = cudaFuncSetAttribute(nucleus_fast_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return e;
-      nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj);
+      RowJob rj1 = rj;
+      if (nucleus_prepass_tma<DT>(rj, st)) rj1.pre_stats = 1;  // max / MUFU mass / candidate threshold at HBM speed
+      nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj1);
       if (!g_no_hist_nucleus) {  // flat rows: radix-select by private histograms, cost independent of the nucleus size
         cudaError_t e3 = cudaFuncSetAttribute(nucleus_hist_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NH_SMEM);
         if (e3 != cudaSuccess) return e3;
@@ -1573,6 +1590,32 @@ static int g_p1_ctas = 3;   // row-kernel CTAs per SM while a tail kernel of the
 static int g_tf_ch = TF_CH_DEFAULT;  // CTAs per sequence of tail_fused_kernel
 static cudaStream_t g_aux_stream = nullptr;
 static cudaEvent_t g_ev_a[8] = {nullptr}, g_ev_b1 = nullptr;
+
+template <int DT>
+static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
+  const size_t es = (DT == DT_F32) ? 4 : 2;
+  const bool ok = DT != DT_F32 && !g_no_tma_nucleus && !g_force_ldg && rj.R > 0 && (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 &&
+                  ((size_t)rj.V * es) % 16 == 0 && ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
+                  ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0;
+  if (!ok) return false;
+  static bool attr_set[3] = {false, false, false};
+  static int occ[3] = {0, 0, 0};
+  if (!attr_set[DT]) {
+    if (cudaFuncSetAttribute(rowfast_tma_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[DT], rowfast_tma_kernel<DT, true>, TS_THREADS, TS_SMEM) != cudaSuccess || occ[DT] < 1)
+      occ[DT] = 1;
+    attr_set[DT] = true;
+  }
+  DecideJob dj;
+  memset(&dj, 0, sizeof(dj));
+  dj.rj = rj;
+  dj.rj.c = rj.c1;  // T = 1 masses
+  HybridWs ws;
+  memset(&ws, 0, sizeof(ws));
+  const long long cap = (long long)(occ[DT] < 4 ? occ[DT] : 4) * num_sms();
+  rowfast_tma_kernel<DT, true><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
+  return cudaGetLastError() == cudaSuccess;
+}
 
 // phase A: row statistics of the job's rows.  limit_ctas > 0 caps the persistent grid per SM.
 template <int DT>
@@ -1847,6 +1890,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   if (!strcmp(name, "no_hist_nucleus")) { g_no_hist_nucleus = value; return 0; }
+  if (!strcmp(name, "no_tma_nucleus")) { g_no_tma_nucleus = value; return 0; }
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
   if (!strcmp(name, "no_fused_tail")) { g_no_fused_tail = value; return 0; }
   return SPECDEC_ERR_ARG;

@@ -467,3 +467,32 @@ def test_verify_step_is_cuda_graph_capturable(oracle_mod, B):
         torch.cuda.synchronize()
         o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
         _assert_same(o, r)
+
+
+@pytest.mark.parametrize("kind,scale", [("peaked", 3.0), ("randn", 3.0), ("randn", 0.1)])
+def test_tma_prepass_of_top_p_rows_changes_nothing(oracle_mod, kind, scale):
+    """optionally, top-p rows get their max / MUFU mass / candidate threshold from a launch of the TMA row pipeline
+    (rowfast_tma_kernel<DT, true>) instead of nucleus_fast_kernel's own first sweep: identical kept sets,
+    probabilities and decisions, and equal to the oracle."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g, V = 6, 3, 128256
+    case = make_case(B=B, gamma=g, V=V, dtype="bf16", sigma=0.3 * scale, seed=91, scale=scale, kind=kind)
+    m = MODES["nucleus0.9_t0.7"]
+    tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(B * g, V),
+                                    torch.rand(B * g, generator=torch.Generator().manual_seed(4)).numpy(), **m)
+    case["draft_tokens"] = torch.from_numpy(tok.reshape(B, g))
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args, **m)
+    p1, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    assert lib.specdec_set_option(b"no_tma_nucleus", 0) == 0  # enable the (optional) TMA pre-pass
+    try:
+        r2 = sd.fused_verify(*args, **m)
+        p2, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    finally:
+        lib.specdec_set_option(b"no_tma_nucleus", 1)
+    assert torch.equal(p1, p2)
+    for a, b_ in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.p_tok, r2.p_tok), (r1.q_tok, r2.q_tok)):
+        assert torch.equal(a, b_)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
+    _assert_same(o, r1)
