@@ -1456,6 +1456,13 @@ static int g_no_tma_nucleus = 1;   // specdec_set_option("no_tma_nucleus", 0) =>
 static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
+// per-device caches (function attributes are per device; one process may drive several GPUs)
+constexpr int MAXDEV = 32;
+static int cur_dev() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < MAXDEV) ? dev : 0;
+}
 static int g_sms = 0;
 static int num_sms() {
   if (g_sms == 0) {
@@ -1588,8 +1595,11 @@ static int g_chunks = 2;    // batch chunks pipelined on two streams (specdec_se
 static int g_chunk0_pct = 50;  // share of the batch in chunk 0 when chunks == 2
 static int g_p1_ctas = 3;   // row-kernel CTAs per SM while a tail kernel of the previous chunk shares the SMs
 static int g_tf_ch = TF_CH_DEFAULT;  // CTAs per sequence of tail_fused_kernel
-static cudaStream_t g_aux_stream = nullptr;
-static cudaEvent_t g_ev_a[8] = {nullptr}, g_ev_b1 = nullptr;
+struct AuxStream {  // per device: the library's high-priority stream for the chunk pipeline + fork/join events
+  cudaStream_t stream;
+  cudaEvent_t ev_a[8], ev_b;
+};
+static AuxStream g_aux[MAXDEV];
 
 template <int DT>
 static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
@@ -1598,13 +1608,12 @@ static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
                   ((size_t)rj.V * es) % 16 == 0 && ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
                   ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0;
   if (!ok) return false;
-  static bool attr_set[3] = {false, false, false};
-  static int occ[3] = {0, 0, 0};
-  if (!attr_set[DT]) {
+  static int occ_dev[MAXDEV];
+  int& occ = occ_dev[cur_dev()];
+  if (!occ) {
     if (cudaFuncSetAttribute(rowfast_tma_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[DT], rowfast_tma_kernel<DT, true>, TS_THREADS, TS_SMEM) != cudaSuccess || occ[DT] < 1)
-      occ[DT] = 1;
-    attr_set[DT] = true;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfast_tma_kernel<DT, true>, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
+      occ = 1;
   }
   DecideJob dj;
   memset(&dj, 0, sizeof(dj));
@@ -1612,7 +1621,7 @@ static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
   dj.rj.c = rj.c1;  // T = 1 masses
   HybridWs ws;
   memset(&ws, 0, sizeof(ws));
-  const long long cap = (long long)(occ[DT] < 4 ? occ[DT] : 4) * num_sms();
+  const long long cap = (long long)(occ < 4 ? occ : 4) * num_sms();
   rowfast_tma_kernel<DT, true><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   return cudaGetLastError() == cudaSuccess;
 }
@@ -1633,18 +1642,15 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
                       ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 &&
                       ((size_t)rj.dsb * es) % 16 == 0 && ((size_t)rj.dsg * es) % 16 == 0 && !g_force_ldg;
   if (tma_ok) {
-    static bool attr_set[3] = {false, false, false};
-    if (!attr_set[DT]) {
+    static int occ_dev[MAXDEV];  // resident CTAs per SM of the persistent grid (0 = attribute not set on this device yet)
+    int& occ = occ_dev[cur_dev()];
+    if (!occ) {
       e = cudaFuncSetAttribute(rowfast_tma_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM);
       if (e != cudaSuccess) return e;
-      attr_set[DT] = true;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfast_tma_kernel<DT>, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
+        occ = 1;
     }
-    static int occ[3] = {0, 0, 0};  // resident CTAs per SM of the persistent grid
-    if (!occ[DT]) {
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[DT], rowfast_tma_kernel<DT>, TS_THREADS, TS_SMEM) != cudaSuccess || occ[DT] < 1)
-        occ[DT] = 1;
-    }
-    const int per_sm = (ctas_per_sm + 1) < occ[DT] ? (ctas_per_sm + 1) : occ[DT];
+    const int per_sm = (ctas_per_sm + 1) < occ ? (ctas_per_sm + 1) : occ;
     const long long cap = (long long)per_sm * num_sms();
     rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   } else {
@@ -1668,11 +1674,19 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
     ws.fused = 1;
     plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
     cudaError_t e;
+    static size_t attr_smem_dev[MAXDEV][2];  // dynamic shared memory already granted (per device, per instantiation)
+    size_t* attr_smem = attr_smem_dev[cur_dev()];
     if (dj.greedy) {
-      if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+      if (attr_smem[1] < tf_smem) {
+        if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+        attr_smem[1] = tf_smem;
+      }
       tail_fused_kernel<DT, true><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
     } else {
-      if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+      if (attr_smem[0] < tf_smem) {
+        if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+        attr_smem[0] = tf_smem;
+      }
       tail_fused_kernel<DT, false><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
     }
     return cudaGetLastError();
@@ -1733,18 +1747,19 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   // latency/issue-bound exact tail of chunk i.  Results do not depend on the split.
   int C = g_chunks;
   if (masked || dj.gamma == 0 || B < 64 * C || C > 8 || DT == DT_F32) C = 1;  // (fp32 rows: LDG row kernel, no gain)
-  if (C > 1 && !g_aux_stream) {
+  AuxStream& ax = g_aux[cur_dev()];
+  if (C > 1 && !ax.stream) {
     // (streams / events cannot be created while the caller's stream is being captured into a CUDA graph)
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) C = 1;
   }
-  if (C > 1 && !g_aux_stream) {
+  if (C > 1 && !ax.stream) {
     int lo = 0, hi = 0;
     cudaDeviceGetStreamPriorityRange(&lo, &hi);
-    if ((e = cudaStreamCreateWithPriority(&g_aux_stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
+    if ((e = cudaStreamCreateWithPriority(&ax.stream, cudaStreamNonBlocking, hi)) != cudaSuccess) return e;
     for (int i = 0; i < 8; ++i)
-      if ((e = cudaEventCreateWithFlags(&g_ev_a[i], cudaEventDisableTiming)) != cudaSuccess) return e;
-    if ((e = cudaEventCreateWithFlags(&g_ev_b1, cudaEventDisableTiming)) != cudaSuccess) return e;
+      if ((e = cudaEventCreateWithFlags(&ax.ev_a[i], cudaEventDisableTiming)) != cudaSuccess) return e;
+    if ((e = cudaEventCreateWithFlags(&ax.ev_b, cudaEventDisableTiming)) != cudaSuccess) return e;
   }
   if (g_ev[0]) cudaEventRecord(g_ev[0], st);
   if (C == 1) {
@@ -1766,13 +1781,13 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
         if (g_ev[1]) cudaEventRecord(g_ev[1], st);
         if ((e = launch_phase_b<DT>(d, w, b1 - b0, st)) != cudaSuccess) return e;
       } else {
-        cudaEventRecord(g_ev_a[i], st);
-        cudaStreamWaitEvent(g_aux_stream, g_ev_a[i], 0);
-        if ((e = launch_phase_b<DT>(d, w, b1 - b0, g_aux_stream)) != cudaSuccess) return e;
+        cudaEventRecord(ax.ev_a[i], st);
+        cudaStreamWaitEvent(ax.stream, ax.ev_a[i], 0);
+        if ((e = launch_phase_b<DT>(d, w, b1 - b0, ax.stream)) != cudaSuccess) return e;
       }
     }
-    cudaEventRecord(g_ev_b1, g_aux_stream);
-    cudaStreamWaitEvent(st, g_ev_b1, 0);
+    cudaEventRecord(ax.ev_b, ax.stream);
+    cudaStreamWaitEvent(st, ax.ev_b, 0);
   }
   if (g_ev[2]) cudaEventRecord(g_ev[2], st);
   return cudaGetLastError();
