@@ -204,8 +204,15 @@ __device__ void plan_sequence(const DecideJob& job, const HybridWs& ws, int b) {
 }
 
 // one warp per sequence (masked modes / gamma == 0, where no fast row kernel runs)
+// Programmatic dependent launch (PDL): plan_kernel and tail_fused_kernel are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs are scheduled while the previous kernel of the
+// stream drains; griddepcontrol.wait blocks until that kernel has completed and its writes are visible (a no-op
+// for a normal launch).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 template <int DT>
 __global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
+  grid_dependency_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= (int)(job.rj.R / (job.rj.nT + job.rj.nD))) return;
   plan_sequence<DT>(job, ws, b);

@@ -103,7 +103,10 @@ __global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, Hybr
   __shared__ u64 sh_S[2];
   const RowJob& rj = job.rj;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  // (the ticket counter was zeroed by the memset at the head of the call, long before the plan kernel: tickets can
+  // be taken while the plan kernel is still running; its results are only read after the dependency wait)
   if (tid == 0) sh_ticket = atomicAdd(ws.ticket, 1);
+  grid_dependency_wait();
   __syncthreads();
   const int b = sh_ticket / TF_CH, ch = sh_ticket - b * TF_CH;
   const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;

@@ -1455,6 +1455,7 @@ static int g_no_tma_nucleus = 1;   // specdec_set_option("no_tma_nucleus", 0) =>
                                    // second sweep then comes from HBM instead of L2)
 static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
+static int g_no_pdl = 0;         // test hook: specdec_set_option("no_pdl", 1) => plain stream-ordered launches of plan / tail
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 // per-device caches (function attributes are per device; one process may drive several GPUs)
 constexpr int MAXDEV = 32;
@@ -1628,7 +1629,8 @@ static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
 
 // phase A: row statistics of the job's rows.  limit_ctas > 0 caps the persistent grid per SM.
 template <int DT>
-static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B, int ctas_per_sm, cudaStream_t st) {
+static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B, int ctas_per_sm, cudaStream_t st,
+                                  bool overlap_prev = false) {
   const RowJob& rj = dj.rj;
   const bool masked = rj.top_k > 0 || rj.use_p;
   cudaError_t e;
@@ -1652,6 +1654,19 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
     }
     const int per_sm = (ctas_per_sm + 1) < occ ? (ctas_per_sm + 1) : occ;
     const long long cap = (long long)per_sm * num_sms();
+    if (overlap_prev && !g_no_pdl) {
+      // The row kernel of chunk i > 0 depends on nothing the row kernel of chunk i-1 does (other rows, other
+      // RowOut records): launched with programmatic stream serialization and NO dependency wait, its CTAs start
+      // as the previous row kernel's CTAs drain instead of after its last CTA.
+      cudaLaunchAttribute pdl[1];
+      pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      pdl[0].val.programmaticStreamSerializationAllowed = 1;
+      cudaLaunchConfig_t cfg;
+      memset(&cfg, 0, sizeof(cfg));
+      cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1;
+      cfg.gridDim = dim3((unsigned)(rj.R < cap ? rj.R : cap)); cfg.blockDim = dim3(TS_THREADS); cfg.dynamicSmemBytes = TS_SMEM;
+      return cudaLaunchKernelEx(&cfg, rowfast_tma_kernel<DT>, dj, ws);
+    }
     rowfast_tma_kernel<DT><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   } else {
     rowfast_kernel<DT><<<(unsigned)rj.R, FT, 0, st>>>(dj, ws);
@@ -1672,23 +1687,25 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   const size_t tf_smem = (size_t)spc * TF_SEG_BYTES;
   if (!masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail) {
     ws.fused = 1;
-    plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
     cudaError_t e;
     static size_t attr_smem_dev[MAXDEV][2];  // dynamic shared memory already granted (per device, per instantiation)
     size_t* attr_smem = attr_smem_dev[cur_dev()];
-    if (dj.greedy) {
-      if (attr_smem[1] < tf_smem) {
-        if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
-        attr_smem[1] = tf_smem;
-      }
-      tail_fused_kernel<DT, true><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
-    } else {
-      if (attr_smem[0] < tf_smem) {
-        if ((e = cudaFuncSetAttribute(tail_fused_kernel<DT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
-        attr_smem[0] = tf_smem;
-      }
-      tail_fused_kernel<DT, false><<<(unsigned)B * nch, TF_T, tf_smem, st>>>(dj, ws, spc, nch);
+    auto tail = dj.greedy ? tail_fused_kernel<DT, true> : tail_fused_kernel<DT, false>;
+    if (attr_smem[dj.greedy ? 1 : 0] < tf_smem) {
+      if ((e = cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
+      attr_smem[dj.greedy ? 1 : 0] = tf_smem;
     }
+    // programmatic dependent launches: the CTAs of plan / tail are scheduled while their predecessor drains
+    cudaLaunchAttribute pdl[1];
+    pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    pdl[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1;
+    cfg.gridDim = dim3((unsigned)((B + 7) / 8)); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0;
+    if ((e = cudaLaunchKernelEx(&cfg, plan_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+    cfg.gridDim = dim3((unsigned)B * nch); cfg.blockDim = dim3(TF_T); cfg.dynamicSmemBytes = tf_smem;
+    if ((e = cudaLaunchKernelEx(&cfg, tail, dj, ws, spc, nch)) != cudaSuccess) return e;
     return cudaGetLastError();
   }
   plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
@@ -1776,7 +1793,7 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
       DecideJob d;
       HybridWs w;
       sub_job<DT>(dj, ws, b0, b1 - b0, i, d, w);
-      if ((e = launch_phase_a<DT>(d, w, b1 - b0, i == 0 ? 3 : g_p1_ctas - 1, st)) != cudaSuccess) return e;
+      if ((e = launch_phase_a<DT>(d, w, b1 - b0, i == 0 ? 3 : g_p1_ctas - 1, st, i > 0)) != cudaSuccess) return e;
       if (i == C - 1) {
         if (g_ev[1]) cudaEventRecord(g_ev[1], st);
         if ((e = launch_phase_b<DT>(d, w, b1 - b0, st)) != cudaSuccess) return e;
@@ -1908,6 +1925,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "no_tma_nucleus")) { g_no_tma_nucleus = value; return 0; }
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
   if (!strcmp(name, "no_fused_tail")) { g_no_fused_tail = value; return 0; }
+  if (!strcmp(name, "no_pdl")) { g_no_pdl = value; return 0; }
   return SPECDEC_ERR_ARG;
 }
 
