@@ -391,6 +391,7 @@ template <int DT>
 __global__ void __launch_bounds__(PT, 4) exact_rows_kernel(DecideJob job, HybridWs ws) {
   __shared__ u64 sh64[33];
   __shared__ int sh_last;
+  grid_dependency_wait();
   const RowJob& rj = job.rj;
   const int ntasks = *ws.ntasks;
   for (int tix = blockIdx.x; tix < ntasks; tix += gridDim.x) {  // usually one task per sequence
@@ -636,6 +637,7 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
   __shared__ int shi[33];
   __shared__ long long s_res;
   __shared__ int sh_last;
+  grid_dependency_wait();
   const RowJob& rj = job.rj;
   const int b = blockIdx.x, ch = blockIdx.y, V = rj.V, rps = rj.nT + rj.nD;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;

@@ -1708,16 +1708,23 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
     if ((e = cudaLaunchKernelEx(&cfg, tail, dj, ws, spc, nch)) != cudaSuccess) return e;
     return cudaGetLastError();
   }
-  plan_kernel<DT><<<(B + 7) / 8, 256, 0, st>>>(dj, ws);
-  if (!masked && dj.gamma > 0) exact_rows_kernel<DT><<<dim3((unsigned)B, CH), PT, 0, st>>>(dj, ws);  // tasks are looped over
-  const dim3 grid((unsigned)B, CH);
-  if (masked) {
-    if (dj.greedy) sample_partial_kernel<DT, true, true><<<grid, PT, 0, st>>>(dj, ws);
-    else sample_partial_kernel<DT, true, false><<<grid, PT, 0, st>>>(dj, ws);
-  } else {
-    if (dj.greedy) sample_partial_kernel<DT, false, true><<<grid, PT, 0, st>>>(dj, ws);
-    else sample_partial_kernel<DT, false, false><<<grid, PT, 0, st>>>(dj, ws);
-  }
+  // split pipeline (masked modes, gamma == 0, test hook): plan, [exact sums of the task rows], sampling sweep;
+  // programmatic dependent launches like the fused path
+  cudaLaunchAttribute pdl[1];
+  pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  pdl[0].val.programmaticStreamSerializationAllowed = g_no_pdl ? 0 : 1;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
+  cudaError_t e;
+  cfg.gridDim = dim3((unsigned)((B + 7) / 8)); cfg.blockDim = dim3(256);
+  if ((e = cudaLaunchKernelEx(&cfg, plan_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  cfg.gridDim = dim3((unsigned)B, CH); cfg.blockDim = dim3(PT);
+  if (!masked && dj.gamma > 0)  // tasks are looped over
+    if ((e = cudaLaunchKernelEx(&cfg, exact_rows_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  auto samp = masked ? (dj.greedy ? sample_partial_kernel<DT, true, true> : sample_partial_kernel<DT, true, false>)
+                     : (dj.greedy ? sample_partial_kernel<DT, false, true> : sample_partial_kernel<DT, false, false>);
+  if ((e = cudaLaunchKernelEx(&cfg, samp, dj, ws)) != cudaSuccess) return e;
   return cudaGetLastError();
 }
 
