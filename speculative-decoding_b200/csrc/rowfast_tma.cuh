@@ -101,6 +101,41 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
 // epilogue additionally emits what nucleus_fast_kernel needs to go straight to its candidate sweep -- RowOut.inv =
 // the MUFU mass S (not 1/S), RowOut.cut = candidate threshold (min over the 4-lane-group maxima of the 256 consumer
 // threads: >= 64 elements lie above it), RowOut.Sfix = bits of the mass carried by the 256 per-thread maxima.
+// Maximum of the 8 packed 16-bit elements of one vector, kept PACKED (two lanes): HMNMX2 on bf16x2 / f16x2.
+template <int DT>
+__device__ __forceinline__ unsigned packed_max4(const uint4 raw, unsigned pm) {
+  if (DT == DT_BF16) {
+    __nv_bfloat162 a = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x), *reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+    __nv_bfloat162 b = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&raw.z), *reinterpret_cast<const __nv_bfloat162*>(&raw.w));
+    a = __hmax2(__hmax2(a, b), *reinterpret_cast<const __nv_bfloat162*>(&pm));
+    return *reinterpret_cast<unsigned*>(&a);
+  } else {
+    __half2 a = __hmax2(*reinterpret_cast<const __half2*>(&raw.x), *reinterpret_cast<const __half2*>(&raw.y));
+    __half2 b = __hmax2(*reinterpret_cast<const __half2*>(&raw.z), *reinterpret_cast<const __half2*>(&raw.w));
+    a = __hmax2(__hmax2(a, b), *reinterpret_cast<const __half2*>(&pm));
+    return *reinterpret_cast<unsigned*>(&a);
+  }
+}
+template <int DT>
+__device__ __forceinline__ float packed_max_to_float(unsigned pm) {
+  if (DT == DT_BF16) return fmaxf(__uint_as_float(pm << 16), __uint_as_float(pm & 0xFFFF0000u));
+  const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&pm));
+  return fmaxf(f.x, f.y);
+}
+// sum of the 8 MUFU weights of one 16-bit vector under a maximum m that already covers it (no max logic)
+template <int DT>
+__device__ __forceinline__ void accumulate16(const uint4 raw, const float2 c2, const float2 nmc2, float2& acc) {
+  const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float2 x;
+    if (DT == DT_BF16) { x.x = __uint_as_float(w[k] << 16); x.y = __uint_as_float(w[k] & 0xFFFF0000u); }
+    else x = __half22float2(*reinterpret_cast<const __half2*>(&w[k]));
+    const float2 t = __ffma2_rn(x, c2, nmc2);
+    acc = __fadd2_rn(acc, make_float2(ex2_approx(t.x), ex2_approx(t.y)));
+  }
+}
+
 template <int DT, bool NUC = false>
 __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
   const RowJob& job = dj.rj;
@@ -152,9 +187,27 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
 #pragma unroll
       for (int q = 0; q < VPT; ++q)
         if (tid + q * TS_CONSUMERS < nvec) a[q] = sp[tid + q * TS_CONSUMERS];
+      if (DT == DT_F32) {
 #pragma unroll
-      for (int q = 0; q < VPT; ++q)
-        if (tid + q * TS_CONSUMERS < nvec) online16<DT>(a[q], m, s, c);
+        for (int q = 0; q < VPT; ++q)
+          if (tid + q * TS_CONSUMERS < nvec) online16<DT>(a[q], m, s, c);
+      } else {
+        // 16-bit rows: the maximum of the thread's (up to) VPT vectors of the stage first, on the packed words
+        // (HMNMX2, 4 per vector), ONE rescale test per stage, then the weights without any max logic
+        unsigned pm = (DT == DT_BF16) ? 0xFF80FF80u : 0xFC00FC00u;  // (-inf, -inf)
+#pragma unroll
+        for (int q = 0; q < VPT; ++q)
+          if (tid + q * TS_CONSUMERS < nvec) pm = packed_max4<DT>(a[q], pm);
+        const float vm = packed_max_to_float<DT>(pm);
+        if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
+        const float nmc = -__fmul_rn(m, c);
+        const float2 c2 = make_float2(c, c), nmc2 = make_float2(nmc, nmc);
+        float2 acc = make_float2(s, 0.0f);
+#pragma unroll
+        for (int q = 0; q < VPT; ++q)
+          if (tid + q * TS_CONSUMERS < nvec) accumulate16<DT>(a[q], c2, nmc2, acc);
+        s = __fadd_rn(acc.x, acc.y);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[stage]);
       if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
@@ -163,7 +216,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
     // Scratch is double-buffered by row parity, so one barrier per row suffices.
     float wm = warp_max_f(m);
     const float resc = (m > -INFINITY) ? ex2_approx(__fmul_rn(__fsub_rn(m, wm), c)) : 0.0f;  // weight of my maximum
-    s = __fmul_rn(s, resc);
+    s = (m > -INFINITY) ? __fmul_rn(s, resc) : 0.0f;  // (a thread that saw only -inf carries NaN in s: dropped)
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { sh_m[par][warp] = wm; sh_s[par][warp] = s; }

@@ -496,3 +496,25 @@ def test_tma_prepass_of_top_p_rows_changes_nothing(oracle_mod, kind, scale):
         assert torch.equal(a, b_)
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
     _assert_same(o, r1)
+
+
+@pytest.mark.parametrize("mode", ["multinomial", "nucleus0.9", "topk50"])
+def test_masked_out_vocabulary_regions(oracle_mod, mode):
+    """large contiguous / strided regions of -inf logits (constrained decoding): whole threads, warps and TMA
+    stages of the row kernels see nothing but -inf."""
+    B, g, V = 4, 3, 128256
+    case = make_case(B=B, gamma=g, V=V, dtype="bf16", sigma=0.5, seed=123)
+    t, d = case["target"].float(), case["draft"].float()
+    t[:, :, 1000:70000] = float("-inf"); d[:, :, 1000:70000] = float("-inf")      # a 69k-token hole
+    t[1, :, 8 * 17::8 * 256] = 5.0                                                 # (keeps a few tokens of one thread's stride alive)
+    for k in range(8):                                                             # every vector of consumer thread 5 is -inf
+        t[2, :, (5 * 8 + k)::256 * 8] = float("-inf"); d[2, :, (5 * 8 + k)::256 * 8] = float("-inf")
+    t[3, :, 100000:] = float("-inf"); d[3, :, 90000:] = float("-inf")              # different supports for p and q
+    case["target"], case["draft"] = t.to(torch.bfloat16), d.to(torch.bfloat16)
+    m = MODES[mode]
+    tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(B * g, V),
+                                    torch.rand(B * g, generator=torch.Generator().manual_seed(9)).numpy(), **m)
+    case["draft_tokens"] = torch.from_numpy(tok.reshape(B, g))
+    o, r = _run_both(oracle_mod, case, mode)
+    _assert_same(o, r)
+    assert np.isfinite(r.p_tok.cpu().numpy()).all()
