@@ -97,7 +97,7 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
   }
 }
 
-// NUC = true: pre-pass of the top-p rows (launch_rowstats): the caller passes c = log2(e) (T = 1 masses) and the row
+// MODE 1 (NUC): pre-pass of the top-p rows (launch_rowstats): the caller passes c = log2(e) (T = 1 masses) and the row
 // epilogue additionally emits what nucleus_fast_kernel needs to go straight to its candidate sweep -- RowOut.inv =
 // the MUFU mass S (not 1/S), RowOut.cut = candidate threshold (min over the 4-lane-group maxima of the 256 consumer
 // threads: >= 64 elements lie above it), RowOut.Sfix = bits of the mass carried by the 256 per-thread maxima.
@@ -136,12 +136,18 @@ __device__ __forceinline__ void accumulate16(const uint4 raw, const float2 c2, c
   }
 }
 
-template <int DT, bool NUC = false>
+// MODE 2 (ARGMAX, 16-bit rows): greedy n-gram verify (rowfast_argmax_kernel's job at TMA speed): additionally the first
+// index of the row maximum.  RowOut.Sfix = index | ambiguous << 32; "ambiguous" (the runner-up could be within 4e-6
+// exponent units of the maximum, where the canonical arg-max over the weights may differ from the arg-max over the
+// logits) is decided from the spacing of the 16-bit format at the maximum instead of tracking the runner-up.
+template <int DT, int MODE = 0>
 __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
+  constexpr bool NUC = (MODE == 1), AMAX = (MODE == 2);
   const RowJob& job = dj.rj;
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
   __shared__ float sh_m[2][8], sh_s[2][8], sh_q[2][8], sh_w[2][8];
+  __shared__ unsigned sh_i[2][8];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
   const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
@@ -177,6 +183,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   unsigned phase = 0;
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x, par ^= 1) {
     float m = -INFINITY, s = 0.0f;
+    unsigned first = 0xFFFFFFFFu;  // AMAX: first index of this thread's maximum
     for (int k = 0; k < nst; ++k) {
       mbar_wait(&full_bar[stage], phase);
       const unsigned off = (unsigned)k * TS_STAGE_BYTES;
@@ -199,7 +206,25 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
         for (int q = 0; q < VPT; ++q)
           if (tid + q * TS_CONSUMERS < nvec) pm = packed_max4<DT>(a[q], pm);
         const float vm = packed_max_to_float<DT>(pm);
-        if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
+        if (vm > m) {
+          s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c)));
+          m = vm;
+          if (AMAX) {  // rare: locate the first element of the stage that equals the new maximum
+            first = 0xFFFFFFFFu;
+#pragma unroll
+            for (int q = VPT - 1; q >= 0; --q)
+              if (tid + q * TS_CONSUMERS < nvec) {
+                const unsigned w[4] = {a[q].x, a[q].y, a[q].z, a[q].w};
+                const unsigned j0 = ((off >> 4) + (unsigned)(tid + q * TS_CONSUMERS)) * 8u;
+#pragma unroll
+                for (int e = 7; e >= 0; --e) {
+                  const unsigned h = (e & 1) ? (w[e >> 1] >> 16) : (w[e >> 1] & 0xFFFFu);
+                  const float x = (DT == DT_BF16) ? __uint_as_float(h << 16) : __half2float(__ushort_as_half((unsigned short)h));
+                  if (x == vm) first = j0 + (unsigned)e;
+                }
+              }
+          }
+        }
         const float nmc = -__fmul_rn(m, c);
         const float2 c2 = make_float2(c, c), nmc2 = make_float2(nmc, nmc);
         float2 acc = make_float2(s, 0.0f);
@@ -220,6 +245,10 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) { sh_m[par][warp] = wm; sh_s[par][warp] = s; }
+    if (AMAX) {
+      const unsigned wf = __reduce_min_sync(0xffffffffu, (m == wm) ? first : 0xFFFFFFFFu);
+      if (lane == 0) sh_i[par][warp] = wf;
+    }
     if (NUC) {
       float qm = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));  // 4-lane groups: 64 groups of ~V/64 elements,
       qm = fmaxf(qm, __shfl_xor_sync(0xffffffffu, qm, 2));      // the same statistics as nucleus_fast_kernel's own sweep
@@ -250,6 +279,17 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
             Wt += (sh_m[par][w] > -INFINITY) ? __fmul_rn(sh_w[par][w], ex2_approx(__fmul_rn(__fsub_rn(sh_m[par][w], M), c))) : 0.0f;
           }
           o.inv = S; o.cut = th; o.Sfix = (u64)__float_as_uint(Wt);
+        }
+        if (AMAX) {
+          unsigned fi = 0xFFFFFFFFu;
+#pragma unroll
+          for (int w = 0; w < TS_CONSUMERS / 32; ++w)
+            if (sh_m[par][w] == M) fi = min(fi, sh_i[par][w]);
+          // smallest possible gap below M in this 16-bit format: half an ulp of M (M a power of two)
+          const int ex = (int)((__float_as_uint(M) >> 23) & 0xFFu) - ((DT == DT_BF16) ? 8 : 11);
+          const float gap = (ex > 0 && ex < 255) ? __uint_as_float((unsigned)ex << 23) : 0.0f;
+          const bool amb = !(M > -INFINITY) || !(M < INFINITY) || fi >= (unsigned)job.V || !(__fmul_rn(gap, c) >= 4e-6f);
+          o.Sfix = (u64)fi | (amb ? (1ull << 32) : 0ull);
         }
         job.out[r] = o;
       }

@@ -43,7 +43,7 @@ struct RowJob {
   long long R;
   RowOut* out;
   int skip_resolved;  // rowstats_kernel: skip rows whose RowOut is already flagged exact
-  int pre_stats;      // nucleus_fast_kernel: max / MUFU mass / candidate threshold come from rowfast_tma_kernel<DT, true>
+  int pre_stats;      // nucleus_fast_kernel: max / MUFU mass / candidate threshold come from rowfast_tma_kernel<DT, 1>
 };
 
 template <int DT>
@@ -674,7 +674,7 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
     const void* row = row_ptr<DT>(job, r);
     const bool aligned = (((size_t)row) & 15) == 0;
     float m, S1f, th, Wt;
-    if (job.pre_stats) {  // block-uniform: everything sweep 1 produces was emitted by rowfast_tma_kernel<DT, true>
+    if (job.pre_stats) {  // block-uniform: everything sweep 1 produces was emitted by rowfast_tma_kernel<DT, 1>
       const RowOut pre = job.out[r];
       m = pre.m; S1f = pre.inv; th = pre.cut; Wt = __uint_as_float((unsigned)pre.Sfix);
       __syncthreads();  // every thread has read the record before thread 0 overwrites it below
@@ -1456,6 +1456,7 @@ static int g_no_tma_nucleus = 1;   // specdec_set_option("no_tma_nucleus", 0) =>
 static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_no_pdl = 0;         // test hook: specdec_set_option("no_pdl", 1) => plain stream-ordered launches of plan / tail
+static int g_tma_ngram = 0;      // specdec_set_option("tma_ngram", 1) => greedy n-gram verify: arg-max from the TMA row pipeline
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 // per-device caches (function attributes are per device; one process may drive several GPUs)
 constexpr int MAXDEV = 32;
@@ -1612,8 +1613,8 @@ static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
   static int occ_dev[MAXDEV];
   int& occ = occ_dev[cur_dev()];
   if (!occ) {
-    if (cudaFuncSetAttribute(rowfast_tma_kernel<DT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess) return false;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfast_tma_kernel<DT, true>, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
+    if (cudaFuncSetAttribute(rowfast_tma_kernel<DT, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfast_tma_kernel<DT, 1>, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
       occ = 1;
   }
   DecideJob dj;
@@ -1623,7 +1624,32 @@ static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st) {
   HybridWs ws;
   memset(&ws, 0, sizeof(ws));
   const long long cap = (long long)(occ < 4 ? occ : 4) * num_sms();
-  rowfast_tma_kernel<DT, true><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
+  rowfast_tma_kernel<DT, 1><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
+  return cudaGetLastError() == cudaSuccess;
+}
+
+// greedy n-gram verify: max / MUFU sum / first index of the maximum of every target row through the TMA row pipeline
+template <int DT>
+static bool ngram_argmax_tma(const RowJob& rj, cudaStream_t st) {
+  if (DT == DT_F32 || !g_tma_ngram) return false;
+  const size_t es = 2;
+  const bool ok = !g_force_ldg && rj.R > 0 && (((size_t)rj.tgt) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
+                  ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 && rj.nD == 0;
+  if (!ok) return false;
+  static int occ_dev[MAXDEV];
+  int& occ = occ_dev[cur_dev()];
+  if (!occ) {
+    if (cudaFuncSetAttribute(rowfast_tma_kernel<DT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess) return false;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowfast_tma_kernel<DT, 2>, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
+      occ = 1;
+  }
+  DecideJob dj;
+  memset(&dj, 0, sizeof(dj));
+  dj.rj = rj;
+  HybridWs ws;
+  memset(&ws, 0, sizeof(ws));
+  const long long cap = (long long)(occ < 4 ? occ : 4) * num_sms();
+  rowfast_tma_kernel<DT, 2><<<(unsigned)(rj.R < cap ? rj.R : cap), TS_THREADS, TS_SMEM, st>>>(dj, ws);
   return cudaGetLastError() == cudaSuccess;
 }
 
@@ -1890,7 +1916,8 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
     HybridWs ws = ws_pointers(wl, workspace, B, dj.rj.R);
     if (g_ev[0]) cudaEventRecord(g_ev[0], st);
     DISPATCH_DT(dtype, {
-      rowfast_argmax_kernel<DT><<<(unsigned)dj.rj.R, FT, 0, st>>>(dj.rj);
+      if (!ngram_argmax_tma<DT>(dj.rj, st))  // 16-bit aligned rows: the TMA row pipeline with an arg-max epilogue
+        rowfast_argmax_kernel<DT><<<(unsigned)dj.rj.R, FT, 0, st>>>(dj.rj);
       if (g_ev[1]) cudaEventRecord(g_ev[1], st);
       ngram_greedy_decide_kernel<DT><<<B, PT, 0, st>>>(dj, ws);
       cudaError_t e = cudaGetLastError();
@@ -1933,6 +1960,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
   if (!strcmp(name, "no_fused_tail")) { g_no_fused_tail = value; return 0; }
   if (!strcmp(name, "no_pdl")) { g_no_pdl = value; return 0; }
+  if (!strcmp(name, "tma_ngram")) { g_tma_ngram = value; return 0; }
   return SPECDEC_ERR_ARG;
 }
 

@@ -10,6 +10,7 @@ from cases import MODES, make_case
 pytestmark = pytest.mark.gpu
 
 F_BATCHED, F_NO_BONUS, F_SKIP, F_NGRAM, F_FALLBACK = 1, 2, 4, 8, 16
+TMA_NGRAM_DEFAULT = 0  # library default of the "tma_ngram" option (tests that flip it restore this)
 
 
 def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
@@ -518,3 +519,37 @@ def test_masked_out_vocabulary_regions(oracle_mod, mode):
     o, r = _run_both(oracle_mod, case, mode)
     _assert_same(o, r)
     assert np.isfinite(r.p_tok.cpu().numpy()).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16])
+def test_ngram_greedy_tma_argmax_edge_rows(oracle_mod, dtype):
+    """greedy n-gram verify on 16-bit aligned rows takes max / sum / FIRST index of the maximum from the TMA row
+    pipeline (rowfast_tma_kernel<DT, 2>): maxima at the row ends, tied maxima in different threads' stripes, rows
+    whose maximum is too small for the 16-bit spacing rule (exact fallback), -inf regions."""
+    import specdec_b200 as sd
+    B, g, V = 6, 3, 128256
+    gen = torch.Generator().manual_seed(21)
+    t = 2.0 * torch.randn(B, g + 1, V, generator=gen)
+    t[0, :, 0] = 30.0                                  # maximum at index 0
+    t[1, :, V - 1] = 30.0                              # maximum at the last index
+    t[2, :, 70001] = 25.0; t[2, :, 1234] = 25.0; t[2, :, 99999] = 25.0   # tied maxima: the first index wins
+    t[3] = 0.0                                         # every logit tied at 0 (maximum 0: spacing rule => exact fallback)
+    t[4] = 1e-4 * torch.randn(g + 1, V, generator=gen)  # tiny logits: spacing below the resolution => exact fallback
+    t[5, :, 500:120000] = float("-inf")                # masked-out region
+    tt = t.to(dtype)
+    toks = tt[:, :g].float().argmax(-1)
+    toks[1, 2] = 7; toks[5, 0] = 600                   # a rejected draft; a draft inside the masked region
+    ua = torch.zeros(B, g); us = torch.zeros(B)
+    o = oracle_mod.verify(tt, None, toks, ua, us, greedy=True, flags=F_NGRAM)
+    lib = sd._lib.lib()
+    r2 = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)  # LDG arg-max kernel
+    prev = lib.specdec_set_option(b"tma_ngram", 1)
+    assert prev == 0
+    try:
+        r = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)
+    finally:
+        lib.specdec_set_option(b"tma_ngram", TMA_NGRAM_DEFAULT)
+    _assert_same(o, r, ngram=True)
+    _assert_same(o, r2, ngram=True)
+    assert int(r.next_token[2]) in (1234,) or int(o.n_accepted[2]) < g  # (bonus row of sequence 2: first tied index)
+    assert torch.equal(r.n_accepted, r2.n_accepted) and torch.equal(r.next_token, r2.next_token)
