@@ -106,7 +106,7 @@ SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* e
  *  "no_fast_ngram"=1 [0]    greedy n-gram verify takes the exact kernels;
  *  "no_fused_tail"=1 [0]    exact_rows + sample_partial kernels instead of tail_fused_kernel;
  *  "no_pdl"=1 [0]           plan / fused tail launched without programmatic dependent launch;
- *  "tma_ngram"=1 [0]        greedy n-gram verify on 16-bit rows: max / sum / arg-max from the TMA row pipeline;
+ *  "tma_ngram"=0 [1]        greedy n-gram verify on 16-bit rows: LDG arg-max kernel instead of the TMA row pipeline;
  *  "chunks"=n [2]           batch chunks pipelined on two streams (bf16/fp16, B >= 64 n; 1 = off; "no_overlap"=1 is
  *                           the same as "chunks"=1);  "p1_ctas"=k [3] row-kernel CTAs per SM for chunks > 0;
  *  "tf_ch"=k [20]           CTAs per sequence of tail_fused_kernel. */

@@ -237,7 +237,7 @@ __global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs w
       s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c)));
       m = vm;
     }
-    const float mc = __fmul_rn(m, c);
+    const float mc = (m > -INFINITY) ? __fmul_rn(m, c) : 0.0f;  // (only -inf so far: -inf*c + inf would be NaN)
 #pragma unroll
     for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
   });
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(FT, 2) rowfast_argmax_kernel(RowJob job) {
         }
       }
     }
-    const float mc = __fmul_rn(m, c);
+    const float mc = (m > -INFINITY) ? __fmul_rn(m, c) : 0.0f;  // (only -inf so far: -inf*c + inf would be NaN)
 #pragma unroll
     for (int k = 0; k < 8; ++k) s = __fadd_rn(s, ex2_approx(__fmaf_rn(x[k], c, -mc)));
   });
@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(PT, 4) ngram_greedy_decide_kernel(DecideJob jo
       const int a = (s_tok[i] == toks[i]) ? 1 : 0;
       job.mask[(long long)b * g + i] = (unsigned char)a;
       const float z = load1<DT>(row_ptr<DT>(rj, (long long)b * nT + i), tok);
-      job.p_tok[(long long)b * g + i] = exp2f(__fmaf_rn(z, rj.c, -ro[i].mc)) * ro[i].inv;
+      job.p_tok[(long long)b * g + i] = exp2f(fmaxf(__fmaf_rn(z, rj.c, -ro[i].mc), -125.0f)) * ro[i].inv;  // (canonical clamp: -inf logits)
       job.q_tok[(long long)b * g + i] = 0.0f;
       if (!a && n == g) n = i;
     }
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(PT, 4) ngram_greedy_decide_kernel(DecideJob jo
     job.next_tok[b] = x;
     if (job.next_prob) {
       float np = 0.0f;
-      if (x >= 0) np = exp2f(__fmaf_rn(load1<DT>(row_ptr<DT>(rj, (long long)b * nT + n), (int)x), rj.c, -ro[n].mc)) * ro[n].inv;
+      if (x >= 0) np = exp2f(fmaxf(__fmaf_rn(load1<DT>(row_ptr<DT>(rj, (long long)b * nT + n), (int)x), rj.c, -ro[n].mc), -125.0f)) * ro[n].inv;
       job.next_prob[b] = np;
     }
     if (job.packed) {

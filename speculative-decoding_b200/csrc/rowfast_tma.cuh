@@ -65,7 +65,7 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
                 x3 = __uint_as_float(raw.w);
     const float vm = fmaxf(fmaxf(x0, x1), fmaxf(x2, x3));
     if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
-    const float mc = __fmul_rn(m, c);
+    const float mc = (m > -INFINITY) ? __fmul_rn(m, c) : 0.0f;  // (only -inf so far: -inf*c + inf would be NaN)
     s = __fadd_rn(s, ex2_approx(__fmaf_rn(x0, c, -mc)));
     s = __fadd_rn(s, ex2_approx(__fmaf_rn(x1, c, -mc)));
     s = __fadd_rn(s, ex2_approx(__fmaf_rn(x2, c, -mc)));
@@ -86,7 +86,8 @@ __device__ __forceinline__ void online16(const uint4 raw, float& m, float& s, co
     const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
     if (vm > m) { s = __fmul_rn(s, ex2_approx(__fmul_rn(__fsub_rn(m, vm), c))); m = vm; }
     // packed fp32x2 (FFMA2 / FADD2): half the issue slots for the exponent arguments and the accumulation
-    const float2 c2 = make_float2(c, c), nmc2 = make_float2(-__fmul_rn(m, c), -__fmul_rn(m, c));
+    const float nmc_ = (m > -INFINITY) ? -__fmul_rn(m, c) : 0.0f;
+    const float2 c2 = make_float2(c, c), nmc2 = make_float2(nmc_, nmc_);
     float2 acc = make_float2(s, 0.0f);
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -225,7 +226,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
               }
           }
         }
-        const float nmc = -__fmul_rn(m, c);
+        const float nmc = (m > -INFINITY) ? -__fmul_rn(m, c) : 0.0f;  // (a thread that has only seen -inf: no NaN)
         const float2 c2 = make_float2(c, c), nmc2 = make_float2(nmc, nmc);
         float2 acc = make_float2(s, 0.0f);
 #pragma unroll

@@ -684,7 +684,7 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
       sweep<DT>(row, V, aligned, [&](const float(&x)[8], int) {
         const float vm = fmaxf(fmaxf(fmaxf(x[0], x[1]), fmaxf(x[2], x[3])), fmaxf(fmaxf(x[4], x[5]), fmaxf(x[6], x[7])));
         if (vm > tm) { ts = __fmul_rn(ts, ex2_approx(__fmul_rn(__fsub_rn(tm, vm), c1))); tm = vm; }
-        const float mcl = __fmul_rn(tm, c1);
+        const float mcl = (tm > -INFINITY) ? __fmul_rn(tm, c1) : 0.0f;  // (only -inf so far: no NaN)
 #pragma unroll
         for (int k = 0; k < 8; ++k) ts = __fadd_rn(ts, ex2_approx(__fmaf_rn(x[k], c1, -mcl)));
       });
@@ -1456,7 +1456,7 @@ static int g_no_tma_nucleus = 1;   // specdec_set_option("no_tma_nucleus", 0) =>
 static int g_no_hist_nucleus = 0;  // test hook: specdec_set_option("no_hist_nucleus", 1) => band search for flat rows
 static int g_force_ldg = 0;  // test hook: specdec_set_option("force_ldg", 1)
 static int g_no_pdl = 0;         // test hook: specdec_set_option("no_pdl", 1) => plain stream-ordered launches of plan / tail
-static int g_tma_ngram = 0;      // specdec_set_option("tma_ngram", 1) => greedy n-gram verify: arg-max from the TMA row pipeline
+static int g_tma_ngram = 1;      // greedy n-gram verify on 16-bit rows: arg-max from the TMA row pipeline ("tma_ngram"=0: LDG kernel)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 // per-device caches (function attributes are per device; one process may drive several GPUs)
 constexpr int MAXDEV = 32;

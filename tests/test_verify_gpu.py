@@ -10,7 +10,7 @@ from cases import MODES, make_case
 pytestmark = pytest.mark.gpu
 
 F_BATCHED, F_NO_BONUS, F_SKIP, F_NGRAM, F_FALLBACK = 1, 2, 4, 8, 16
-TMA_NGRAM_DEFAULT = 0  # library default of the "tma_ngram" option (tests that flip it restore this)
+TMA_NGRAM_DEFAULT = 1  # library default of the "tma_ngram" option (tests that flip it restore this)
 
 
 def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
@@ -542,10 +542,10 @@ def test_ngram_greedy_tma_argmax_edge_rows(oracle_mod, dtype):
     ua = torch.zeros(B, g); us = torch.zeros(B)
     o = oracle_mod.verify(tt, None, toks, ua, us, greedy=True, flags=F_NGRAM)
     lib = sd._lib.lib()
-    r2 = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)  # LDG arg-max kernel
-    prev = lib.specdec_set_option(b"tma_ngram", 1)
-    assert prev == 0
+    assert lib.specdec_set_option(b"tma_ngram", 0) == 0
     try:
+        r2 = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)  # LDG arg-max kernel
+        assert lib.specdec_set_option(b"tma_ngram", 1) == 0
         r = sd.fused_verify(tt.cuda(), None, toks.cuda(), ua.cuda(), us.cuda(), greedy=True, flags=F_NGRAM)
     finally:
         lib.specdec_set_option(b"tma_ngram", TMA_NGRAM_DEFAULT)
