@@ -212,6 +212,7 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 
 template <int DT>
 __global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // the tail's CTAs may start taking their tickets
   grid_dependency_wait();
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= (int)(job.rj.R / (job.rj.nT + job.rj.nD))) return;

@@ -145,6 +145,9 @@ template <int DT, int MODE = 0>
 __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj, HybridWs ws) {
   constexpr bool NUC = (MODE == 1), AMAX = (MODE == 2);
   const RowJob& job = dj.rj;
+  // PDL: let the next kernel of the stream (the row kernel of the next chunk, which never waits, or plan_kernel, which
+  // does) be scheduled as soon as SM resources free up instead of after this grid's last CTA
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(128) unsigned char ring[];
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
   __shared__ float sh_m[2][8], sh_s[2][8], sh_q[2][8], sh_w[2][8];
