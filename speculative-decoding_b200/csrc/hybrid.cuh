@@ -225,6 +225,7 @@ __global__ void __launch_bounds__(256) plan_kernel(DecideJob job, HybridWs ws) {
 template <int DT>
 __global__ void __launch_bounds__(FT, 2) rowfast_kernel(DecideJob dj, HybridWs ws) {
   __shared__ float shf[33];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: plan_kernel may be scheduled early (it waits)
   const RowJob& job = dj.rj;
   const long long r = blockIdx.x;
   const void* row = row_ptr<DT>(job, r);

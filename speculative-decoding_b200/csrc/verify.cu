@@ -410,6 +410,7 @@ __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw
 // ---------------------------------------------------------------------------------------------
 template <int DT, bool HK, bool HP>
 __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // PDL: plan_kernel may be scheduled early (it waits)
   // specialised per mask type so that each instantiation only carries its own code path
   RowJob job = job_in;
   if (!HK) job.top_k = 0;
