@@ -114,6 +114,11 @@ SPECDEC_API int specdec_set_option(const char* name, int value);
 /* Test hook: copies 16 device-side counters of nucleus_hist_kernel to out16 (host memory; synchronises):
  * [0..6] failed attempts by reason, [7] rows left to the slow path, [8] rows resolved, [9] attempts. */
 SPECDEC_API int specdec_debug_stats(unsigned long long* out16, int reset);
+/* Tuning hook: with option "mega_dbg"=1 the persistent verify kernel stamps %globaltimer (ns) into its workspace:
+ * [0] first CTA start, [1] last row-streaming CTA done, [2] last CTA done, [3] first row-streaming CTA done, then 8 per
+ * sequence: plan start, plan published, first / last exact item started, normalisers complete, finalize start / end.
+ * Copies min(n, 16 + 8 B) values to host_out (synchronises the device). */
+SPECDEC_API int specdec_debug_timeline(const void* workspace, int B, int gamma, int V, unsigned long long* host_out, int n);
 
 /* LogitsProcessor.__call__ materialised: probs[rows,V] fp32 = softmax(_process(logits)/T)
  * (utils/logits_processor.py:13-15).  row_stats (nullable) receives 8 floats per row:

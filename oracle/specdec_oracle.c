@@ -263,10 +263,19 @@ ORACLE_API int oracle_verify(const float* tgt, const float* drf, int B, int gamm
       if (!acc && n == gamma) n = i;
     }
     n_acc[b] = n;
+    /* sampling/speculative_decoding.py:150-152: torch.nonzero(eq(ids[1,n], stop[k,1]))[0,1] -- the first-LISTED stop
+     * token that occurs among the accepted drafts decides (first position of it); the batched engine
+     * (engine/infer_engine.py:310-312) breaks at the earliest accepted position holding any end token. */
     int fs = -1;
-    for (int i = 0; i < n && fs < 0; ++i)
-      for (int k = 0; k < n_stop; ++k)
-        if (draft_tokens[(int64_t)b * gamma + i] == stop[k]) { fs = i; break; }
+    if (flags & F_ACCEPT_BATCHED) {
+      for (int i = 0; i < n && fs < 0; ++i)
+        for (int k = 0; k < n_stop; ++k)
+          if (draft_tokens[(int64_t)b * gamma + i] == stop[k]) { fs = i; break; }
+    } else {
+      for (int k = 0; k < n_stop && fs < 0; ++k)
+        for (int i = 0; i < n; ++i)
+          if (draft_tokens[(int64_t)b * gamma + i] == stop[k]) { fs = i; break; }
+    }
     first_stop[b] = fs;
     float us = u_sample[b];
     int64_t x;

@@ -12,6 +12,11 @@ import torch
 from torch.nn import functional as F
 
 
+# torch.sort's order of EQUAL logits is unspecified (it differs between torch builds / thread counts); the parity
+# harness pins it to the stable order, exactly as oracle/ref_harness.py:stable_sort() does for the imported reference.
+STABLE_SORT = False
+
+
 def _process(logits, mode):
     k, p = mode["top_k"], mode["top_p"]
     if k and k > 0:  # utils/logits_processor.py:59-63 (the reference mutates in place; callers clone)
@@ -20,7 +25,7 @@ def _process(logits, mode):
         logits = logits.clone()
         logits[rm] = -1e20
     if p is not None and 0.0 < p < 1.0:  # utils/logits_processor.py:73-81
-        sorted_logits, sorted_indices = torch.sort(logits, descending=True)
+        sorted_logits, sorted_indices = torch.sort(logits, descending=True, stable=STABLE_SORT)
         cumulative_probs = torch.cumsum(F.softmax(sorted_logits, dim=-1), dim=-1)
         rem = cumulative_probs > p
         rem[..., 1:] = rem[..., :-1].clone()
@@ -54,8 +59,21 @@ def sample_rows(draft_logits, mode, gen=None):
                         range(draft_logits.shape[0])])
 
 
-def verify_one(t_logits, d_logits, toks, mode, gen=None, r=None, skip_sample_adjustment=False):
-    """One verify step of one sequence: t_logits [g+1,V], d_logits [g,V], toks [g] -> (n, x)."""
+def inv_cdf64(probs, u):
+    """sample() restated as inverse CDF on an injected uniform: float64 cumulative sums of the
+    reference's fp32 probabilities, first index whose cumulative mass exceeds u * total."""
+    p = probs.detach().double().reshape(-1).clamp_min(0)
+    cum = torch.cumsum(p, 0)
+    j = int(torch.searchsorted(cum, torch.tensor(float(u) * float(cum[-1]), dtype=torch.float64), right=True))
+    nz = torch.nonzero(p > 0).reshape(-1)
+    return min(j, int(nz[-1])) if nz.numel() else 0
+
+
+def verify_one(t_logits, d_logits, toks, mode, gen=None, r=None, skip_sample_adjustment=False, u_sample=None,
+               want_detail=False):
+    """One verify step of one sequence: t_logits [g+1,V], d_logits [g,V], toks [g] -> (n, x).
+    u_sample: the final sample() as inverse CDF on this uniform instead of torch.multinomial;
+    want_detail: also return (fractions at the draft tokens [g], p_p)."""
     g, V = d_logits.shape
     q = torch.zeros((1, g, V))                                    # :107 (fp32)
     for k in range(g):
@@ -75,5 +93,10 @@ def verify_one(t_logits, d_logits, toks, mode, gen=None, r=None, skip_sample_adj
         p_p = max_fn(p[..., n, :] - q[0, n, :])                   # :168
     else:
         p_p = p[..., n, :]
-    x = sample(p_p, mode, gen)                                    # :171
-    return n, int(x.reshape(-1)[0])
+    if u_sample is not None and not mode["greedy"]:
+        x = inv_cdf64(p_p, u_sample)
+    else:
+        x = int(sample(p_p, mode, gen).reshape(-1)[0])            # :171
+    if want_detail:
+        return n, x, fractions[0, torch.arange(g), toks].clone(), p_p.reshape(-1)
+    return n, x

@@ -25,6 +25,7 @@ _SIGS = {
                             _f, _i, _f, _i, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "specdec_set_profile_events": (_i, [_vp, _vp, _vp]),
     "specdec_debug_stats": (_i, [_vp, _i]),
+    "specdec_debug_timeline": (_i, [_vp, _i, _i, _i, _vp, _i]),
     "specdec_set_option": (_i, [C.c_char_p, _i]),
     "specdec_process_probs": (_i, [_vp, _i, _i64, _i, _i64, _f, _i, _f, _vp, _vp, _vp, _sz, _vp]),
     "specdec_sample_rows": (_i, [_vp, _i, _i64, _i, _i64, _f, _i, _f, _i, _vp, _u64, _u64, _i64, _i, _vp, _vp,

@@ -240,7 +240,18 @@ __device__ __forceinline__ void unpack8(const Raw8<DT>& r, float (&x)[8]) {
   }
 }
 
-// ---- block-wide reductions for NT = 1024 threads (32 warps); `sh` = 33-entry scratch ----
+// ---- the CTA's compute group ----
+// Ordinary kernels: all threads of the CTA, __syncthreads().  CTAs of exactly 288 threads are warp-specialised
+// (rowfast_tma_kernel, verify_mega_kernel): warps 0-7 form the compute group (named barrier 1, 256 threads), warp 8 is
+// a service warp (TMA producer / planner) that never calls the block-wide helpers below.
+constexpr int WS_CTA_THREADS = 288, WS_COMPUTE_THREADS = 256;
+__device__ __forceinline__ int cta_nthreads() { return blockDim.x == WS_CTA_THREADS ? WS_COMPUTE_THREADS : (int)blockDim.x; }
+__device__ __forceinline__ void cta_sync() {
+  if (blockDim.x == WS_CTA_THREADS) asm volatile("bar.sync 1, %0;" ::"n"(WS_COMPUTE_THREADS) : "memory");
+  else __syncthreads();
+}
+
+// ---- block-wide reductions (up to 32 warps); `sh` = 33-entry scratch ----
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -259,42 +270,42 @@ __device__ __forceinline__ float warp_min_f(float v) {
 // All threads get the result.  Two barriers; safe to call back to back with the same scratch.
 __device__ __forceinline__ u64 block_sum_u64(u64 v, u64* sh) {
   v = warp_sum_u64(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (cta_nthreads() + 31) >> 5;
   if (lane == 0) sh[w] = v;
-  __syncthreads();
+  cta_sync();
   u64 t = (lane < nw) ? sh[lane] : 0ull;
   t = warp_sum_u64(t);
-  __syncthreads();
+  cta_sync();
   return t;
 }
 __device__ __forceinline__ float block_max_f(float v, float* sh) {
   v = warp_max_f(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (cta_nthreads() + 31) >> 5;
   if (lane == 0) sh[w] = v;
-  __syncthreads();
+  cta_sync();
   float t = (lane < nw) ? sh[lane] : -INFINITY;
   t = warp_max_f(t);
-  __syncthreads();
+  cta_sync();
   return t;
 }
 __device__ __forceinline__ float block_min_f(float v, float* sh) {
   v = warp_min_f(v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (cta_nthreads() + 31) >> 5;
   if (lane == 0) sh[w] = v;
-  __syncthreads();
+  cta_sync();
   float t = (lane < nw) ? sh[lane] : INFINITY;
   t = warp_min_f(t);
-  __syncthreads();
+  cta_sync();
   return t;
 }
 __device__ __forceinline__ unsigned block_min_u32(unsigned v, unsigned* sh) {
   v = __reduce_min_sync(0xffffffffu, v);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (cta_nthreads() + 31) >> 5;
   if (lane == 0) sh[w] = v;
-  __syncthreads();
+  cta_sync();
   unsigned t = (lane < nw) ? sh[lane] : 0xFFFFFFFFu;
   t = __reduce_min_sync(0xffffffffu, t);
-  __syncthreads();
+  cta_sync();
   return t;
 }
 

@@ -24,6 +24,9 @@ constexpr int CH = 8;     // CTAs per row (pair) in exact_rows / sample_partial
 constexpr int ST_ACCEPT = 0, ST_REJECT = 1, ST_AMBIG = 2, ST_EXACTROW = 3, ST_NEED = 4;
 constexpr float MARGIN = 1e-3f;
 constexpr int SAMP_N = 8;  // ints per sequence in HybridWs::samp
+constexpr int MG_MAXU = 8;  // megakernel: slices per logit row
+constexpr int MG_SM_SLOTS = 256;  // megakernel: >= number of SM ids
+constexpr int MG_MIN_SPC = 12;  // megakernel: smallest exact item (256-element segments); sizes the slot array
 
 struct HybridWs {
   u64* acc;               // [R]  canonical Sfix of task rows
@@ -33,7 +36,7 @@ struct HybridWs {
   u64* part;              // [B][nseg_pad]
   u64* tot;               // [B]
   u64* best;              // [B]  greedy: (value bits << 32) | ~index
-  int* samp;              // [B][SAMP_N]: n, mode, p-row position, bits of mc of the p row, of the q row
+  int* samp;              // [B][SAMP_N]: n, mode, p-row position, bits of mc of the p row, of the q row, exact tasks
   int* rows_done;         // [B]  rows of the sequence whose statistics are written
   int* seq_tasks;         // [B]  number of exact tasks of the sequence
   int* exact_done;        // [B]
@@ -42,10 +45,58 @@ struct HybridWs {
   int* fin_done;          // [B]     fused tail: CTAs whose partial sums are in acc2
   int* decided;           // [B]     fused tail: set once CTA 0 of the group has decided the sequence
   int* ticket;            // [2]     fused tail: logical CTA ids in dispatch order (one counter per half batch)
+  int* abort;             // [1]     set when a bounded inter-CTA wait gave up (see spin_until)
+  int* plan_done;         // [B]     megakernel: the sequence's plan record is published
+  int* x_next;            // [1]     megakernel: next exact item (sequence-major, claimed in order)
+  int* p_next;            // [1]     megakernel: next sequence to plan
+  float2* rpart;          // [R][MG_MAXU]  megakernel: (max, MUFU sum relative to it) of every row slice
+  int* sm_slots;          // [MG_SM_SLOTS]  megakernel: CTAs that arrived per SM (role assignment)
+  int* r_ticket;          // [2]     megakernel: R lane / X rank tickets
+  u64* xs;                // [B][xs_stride][4]  megakernel: per exact item {Sfix_p part, Sfix_q part, greedy key, -} | WORD_VALID
+  int xs_stride;
+  u64* dbg;               // nullable: [16 + B * 8] %globaltimer stamps of the megakernel (option "mega_dbg")
   int fused;              // plan: the first sure reject is handled by tail_fused_kernel, not as an exact task
   int nseg_pad;
 };
 
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded wait for *p >= target.  `abort` (a word in the zeroed part of the workspace) turns a wait that can never be
+// satisfied -- sibling CTAs that were not co-scheduled (MPS / sanitizer / a debugger serialising CTAs) -- into an
+// error instead of a hang: after ~2^22 polls the waiter sets it, every other waiter sees it and leaves, the kernel
+// terminates and specdec_verify_status() reports SPECDEC_ERR_TIMEOUT.
+__device__ __forceinline__ bool spin_until(const int* p, int target, int* abort) {
+  for (unsigned it = 1;; ++it) {
+    if (ld_acquire_gpu(p) >= target) return true;
+    if ((it & 255u) == 0u && abort) {
+      if (ld_acquire_gpu(abort) != 0) return false;
+      if (it > (1u << 22)) { atomicExch(abort, 1); return false; }
+    }
+    __nanosleep(40);
+  }
+}
+// L2-coherent reads of records other CTAs of the SAME launch wrote (a persistent CTA may hold stale L1 lines)
+__device__ __forceinline__ RowOut ldcg_rowout(const RowOut* p) {
+  const int4 a = __ldcg(reinterpret_cast<const int4*>(p)), b = __ldcg(reinterpret_cast<const int4*>(p) + 1);
+  RowOut o;
+  o.m = __int_as_float(a.x); o.mc = __int_as_float(a.y); o.inv = __int_as_float(a.z); o.cut = __int_as_float(a.w);
+  o.jcut = b.x; o.flags = b.y;
+  o.Sfix = ((u64)(unsigned)b.w << 32) | (u64)(unsigned)b.z;
+  return o;
+}
+
+__device__ __forceinline__ u64 global_timer_ns() {
+  u64 t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// debug timeline (HybridWs::dbg): global slots 0..15, then 8 per sequence
+__device__ __forceinline__ void dbg_stamp_min(const HybridWs& ws, int slot) { if (ws.dbg) atomicMin(&ws.dbg[slot], global_timer_ns()); }
+__device__ __forceinline__ void dbg_stamp_max(const HybridWs& ws, int slot) { if (ws.dbg) atomicMax(&ws.dbg[slot], global_timer_ns()); }
 
 __device__ __forceinline__ float job_u_accept(const DecideJob& job, int b, int i) {
   return job.u_accept ? job.u_accept[(long long)b * job.gamma + i]
@@ -62,7 +113,7 @@ __device__ __forceinline__ int accept_rule(float p, float q, float u, int flags)
 
 // exact statistics of row r: from rowstats_kernel (masked modes) or from the exact task sums
 __device__ __forceinline__ RowOut resolved_row(const RowJob& rj, const HybridWs& ws, long long r) {
-  RowOut o = rj.out[r];
+  RowOut o = ldcg_rowout(&rj.out[r]);
   if (!(o.flags & 1)) {
     const u64 S = __ldcg(&ws.acc[r]);
     o.Sfix = S;
@@ -84,7 +135,7 @@ __device__ void decide_sequence(const DecideJob& job, const HybridWs& ws, int b)
     const int i = i0 + lane;
     int a = 1;
     if (i < g) {
-      const int st = ws.status[(long long)b * g + i];
+      const int st = __ldcg(&ws.status[(long long)b * g + i]);  // (possibly written by another CTA of this launch)
       if ((st & ST_NEED) || (st & 3) == ST_EXACTROW) {
         const int rps = rj.nT + rj.nD;
         const int tok = (int)min(max(toks[i], 0ll), (long long)rj.V - 1);
@@ -109,17 +160,14 @@ __device__ void decide_sequence(const DecideJob& job, const HybridWs& ws, int b)
       if (!(job.flags & SPECDEC_NO_BONUS)) { mode = 1; prow = g; }
     } else if (job.flags & SPECDEC_SKIP_ADJUST) { mode = 1; prow = n; }
     else { mode = 2; prow = n; }
-    int fs = -1;
-    for (int i = 0; i < n && fs < 0; ++i)
-      for (int k = 0; k < job.n_stop; ++k)
-        if (toks[i] == job.stop[k]) { fs = i; break; }
+    const int fs = first_stop_index(toks, n, job.stop, job.n_stop, job.flags);
     job.n_acc[b] = n;
     job.first_stop[b] = fs;
     ws.samp[b * SAMP_N + 0] = n; ws.samp[b * SAMP_N + 1] = mode; ws.samp[b * SAMP_N + 2] = prow;
     if (mode) {  // one record read gives tail_fused_kernel everything it needs to start streaming
       const int rps = rj.nT + rj.nD;
-      ws.samp[b * SAMP_N + 3] = __float_as_int(rj.out[(long long)b * rps + prow].mc);
-      ws.samp[b * SAMP_N + 4] = (mode == 2) ? __float_as_int(rj.out[(long long)b * rps + rj.nT + prow].mc) : 0;
+      ws.samp[b * SAMP_N + 3] = __float_as_int(ldcg_rowout(&rj.out[(long long)b * rps + prow]).mc);
+      ws.samp[b * SAMP_N + 4] = (mode == 2) ? __float_as_int(ldcg_rowout(&rj.out[(long long)b * rps + rj.nT + prow]).mc) : 0;
     }
     if (mode == 0) {  // nothing to sample (all accepted, no bonus token)
       job.next_tok[b] = -1;
@@ -195,7 +243,7 @@ __device__ void plan_sequence(const DecideJob& job, const HybridWs& ws, int b) {
     }
     ntask += __popc(__ballot_sync(0xffffffffu, need));
   }
-  if (lane == 0) ws.seq_tasks[b] = ntask;
+  if (lane == 0) { ws.seq_tasks[b] = ntask; ws.samp[b * SAMP_N + 5] = ntask; }
   __syncwarp();
   if (ntask == 0) {  // nothing to make exact: decide right away
     __threadfence();
@@ -361,10 +409,7 @@ __global__ void __launch_bounds__(PT, 4) ngram_greedy_decide_kernel(DecideJob jo
       job.q_tok[(long long)b * g + i] = 0.0f;
       if (!a && n == g) n = i;
     }
-    int fs = -1;
-    for (int i = 0; i < n && fs < 0; ++i)
-      for (int k = 0; k < job.n_stop; ++k)
-        if (toks[i] == job.stop[k]) { fs = i; break; }
+    const int fs = first_stop_index(toks, n, job.stop, job.n_stop, job.flags);
     const long long x = (n < nT) ? s_tok[n] : -1ll;  // argmax(p_n), or the bonus row; -1 without a bonus row
     job.n_acc[b] = n;
     job.first_stop[b] = fs;
@@ -569,7 +614,7 @@ __device__ void finalize_sequence(const DecideJob& job, const HybridWs& ws, int 
 template <int DT, bool MASKED, bool GREEDY, bool RESID>
 __device__ __forceinline__ void partial_loop(const void* prowp, const void* qrowp, const RowOut& rp, const RowOut& rq,
                                              bool pal, bool qal, int V, float c, int s0, int s1, u64* part, u64& tot,
-                                             float& best, int& bidx) {
+                                             float& best, int& bidx, const u64 vflag = 0ull) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int NV = (V + 7) >> 3;
   const float mcp = rp.mc, mcq = rq.mc, invp = rp.inv, invq = rq.inv;
@@ -623,7 +668,7 @@ __device__ __forceinline__ void partial_loop(const void* prowp, const void* qrow
       const int sg = seg + q * WPB;
       if (sg < s1) {  // warp-uniform
         const u64 sa = warp_sum_u64(sums[q]);
-        if (lane == 0) { part[sg] = sa; tot += sa; }
+        if (lane == 0) { part[sg] = sa | vflag; tot += sa; }
       }
     }
   }
@@ -691,3 +736,4 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
 }
 
 #include "tail_fused.cuh"
+#include "mega.cuh"

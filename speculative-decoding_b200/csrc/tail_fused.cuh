@@ -20,14 +20,6 @@ constexpr int TF_CH_DEFAULT = 20;  // CTAs per sequence (52 KB of weights per CT
 constexpr int TF_T = 256;   // threads per CTA (== PT: partial_loop assumes it)
 constexpr int TF_SEG_BYTES = 2048;  // one 256-pair segment of (e_p, e_q)
 
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void spin_until(const int* p, int target) {
-  while (ld_acquire_gpu(p) < target) __nanosleep(40);
-}
 // row k (target rows first, then drafter rows) of sequence b, without row_ptr's 64-bit division
 template <int DT>
 __device__ __forceinline__ const void* seq_row_ptr(const RowJob& job, int b, int k) {
@@ -39,25 +31,25 @@ __device__ __forceinline__ const void* seq_row_ptr(const RowJob& job, int b, int
 __device__ __forceinline__ void block_sum2_u64(u64& a, u64& b, u64* sh) {
   a = warp_sum_u64(a);
   b = warp_sum_u64(b);
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (cta_nthreads() + 31) >> 5;
   if (lane == 0) { sh[w] = a; sh[33 + w] = b; }
-  __syncthreads();
+  cta_sync();
   u64 t = (lane < nw) ? sh[lane] : 0ull, u = (lane < nw) ? sh[33 + lane] : 0ull;
   a = warp_sum_u64(t);
   b = warp_sum_u64(u);
-  __syncthreads();
+  cta_sync();
 }
 
 // Canonical sums of segments [s0, s1) of a row pair; CACHE: also keep (e_p, e_q) in shared memory as
 // float4 {e_p[2k], e_q[2k], e_p[2k+1], e_q[2k+1]} at [(seg - s0) * 128 + k * 32 + lane] (conflict-free).
-template <int DT, bool CACHE>
+template <int DT, bool CACHE, int NS_ = 0>
 __device__ __forceinline__ void pair_sums(const void* prow, const void* qrow, bool pal, bool qal, int V, float c,
                                           float mcp, float mcq, int s0, int s1, float4* ecache, u64& sp, u64& sq) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int NV = (V + 7) >> 3;
   const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mcp, -mcq);
   constexpr int WPB = TF_T / 32;
-  constexpr int NS = (DT == DT_F32) ? 2 : 4;  // segments in flight per warp (raw, still packed loads)
+  constexpr int NS = NS_ ? NS_ : ((DT == DT_F32) ? 2 : 4);  // segments in flight per warp (raw, still packed loads)
   for (int seg = s0 + w; seg < s1; seg += NS * WPB) {
     Raw8<DT> rp[NS], rq[NS];
 #pragma unroll
@@ -92,39 +84,40 @@ __device__ __forceinline__ void pair_sums(const void* prow, const void* qrow, bo
   }
 }
 
+struct TailSh {  // static shared memory of one tail group
+  u64 sh64[66];
+  float shf[33];
+  int shi[33];
+  long long s_res;
+  int sh_last, sh_ok;
+  u64 sh_S[2];
+};
+
+// Everything after the plan for slice `ch` (of TF_CH) of sequence b.  Called by all threads of the CTA's compute group
+// (cta_nthreads() threads, cta_sync() barriers; work loops use the first TF_T of them).  Returns false iff a bounded
+// inter-CTA wait gave up (ws.abort is then set and the caller leaves the kernel).
 template <int DT, bool GREEDY>
-__global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, HybridWs ws, int segs_per_cta, int TF_CH) {
-  extern __shared__ __align__(16) float4 ecache[];
-  __shared__ u64 sh64[66];
-  __shared__ float shf[33];
-  __shared__ int shi[33];
-  __shared__ long long s_res;
-  __shared__ int sh_ticket, sh_last;
-  __shared__ u64 sh_S[2];
+__device__ __forceinline__ bool tail_item(const DecideJob& job, const HybridWs& ws, const int b, const int ch, const int TF_CH,
+                                          const int segs_per_cta, float4* ecache, TailSh& sh, const int seq_tasks,
+                                          const bool have_rec, int4 rec, int mcq_bits) {
   const RowJob& rj = job.rj;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
-  // (the ticket counter was zeroed by the memset at the head of the call, long before the plan kernel: tickets can
-  // be taken while the plan kernel is still running; its results are only read after the dependency wait)
-  if (tid == 0) sh_ticket = atomicAdd(ws.ticket, 1);
-  grid_dependency_wait();
-  __syncthreads();
-  const int b = sh_ticket / TF_CH, ch = sh_ticket - b * TF_CH;
   const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
   const int NV = (V + 7) >> 3, nseg = (NV + 31) >> 5;
   const int s0 = min(nseg, ch * segs_per_cta), s1 = min(nseg, s0 + segs_per_cta);
   const float c = rj.c;
 
   // ---- rare: exact sums of the ambiguous positions, then CTA 0 of the group decides ----
-  if (ws.seq_tasks[b] > 0) {
+  if (seq_tasks > 0) {
     for (int i = 0; i < g; ++i) {  // block-uniform
-      if ((ws.status[(long long)b * g + i] & 3) != ST_AMBIG) continue;
+      if ((__ldcg((const unsigned char*)&ws.status[(long long)b * g + i]) & 3) != ST_AMBIG) continue;
       const long long r1 = (long long)b * rps + i, r2 = (long long)b * rps + rj.nT + i;
       const void* prow = seq_row_ptr<DT>(rj, b, i);
       const void* qrow = seq_row_ptr<DT>(rj, b, rj.nT + i);
       u64 sp = 0, sq = 0;
-      pair_sums<DT, false>(prow, qrow, (((size_t)prow) & 15) == 0, (((size_t)qrow) & 15) == 0, V, c, rj.out[r1].mc,
-                           rj.out[r2].mc, s0, s1, nullptr, sp, sq);
-      block_sum2_u64(sp, sq, sh64);
+      pair_sums<DT, false>(prow, qrow, (((size_t)prow) & 15) == 0, (((size_t)qrow) & 15) == 0, V, c,
+                           ldcg_rowout(&rj.out[r1]).mc, ldcg_rowout(&rj.out[r2]).mc, s0, s1, nullptr, sp, sq);
+      block_sum2_u64(sp, sq, sh.sh64);
       if (tid == 0) {
         if (sp) atomicAdd(&ws.acc[r1], sp);
         if (sq) atomicAdd(&ws.acc[r2], sq);
@@ -133,26 +126,30 @@ __global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, Hybr
     if (tid == 0) {
       __threadfence();
       atomicAdd(&ws.exact_done[b], 1);
+      sh.sh_ok = 1;
+      if (ch == 0) sh.sh_ok = spin_until(&ws.exact_done[b], TF_CH, ws.abort) ? 1 : 0;
     }
-    if (ch == 0) {
-      if (tid == 0) spin_until(&ws.exact_done[b], TF_CH);
-      __syncthreads();
-      if (tid < 32) {
-        decide_sequence<DT>(job, ws, b);
-        __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicExch(&ws.decided[b], 1);
-        }
+    cta_sync();
+    if (!sh.sh_ok) return false;
+    if (ch == 0 && tid < 32) {
+      decide_sequence<DT>(job, ws, b);
+      __syncwarp();
+      if (lane == 0) {
+        __threadfence();
+        atomicExch(&ws.decided[b], 1);
       }
     }
-    if (tid == 0) spin_until(&ws.decided[b], 1);
-    __syncthreads();
+    if (tid == 0) sh.sh_ok = spin_until(&ws.decided[b], 1, ws.abort) ? 1 : 0;
+    cta_sync();
+    if (!sh.sh_ok) return false;
   }
-  const int4 rec = __ldcg((const int4*)(ws.samp + b * SAMP_N));
+  if (!have_rec || seq_tasks > 0) {  // (the record handed in predates the exact decisions of an ambiguous sequence)
+    rec = __ldcg((const int4*)(ws.samp + b * SAMP_N));
+    mcq_bits = __ldcg(&ws.samp[b * SAMP_N + 4]);
+  }
   const int mode = rec.y, prow_i = rec.z;
-  const float mcp = __int_as_float(rec.w), mcq = __int_as_float(__ldcg(&ws.samp[b * SAMP_N + 4]));
-  if (mode == 0) return;
+  const float mcp = __int_as_float(rec.w), mcq = __int_as_float(mcq_bits);
+  if (mode == 0) return true;
 
   const long long r1 = (long long)b * rps + prow_i;
   const void* prowp = seq_row_ptr<DT>(rj, b, prow_i);
@@ -172,25 +169,27 @@ __global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, Hybr
     // ---- phase A: canonical weights of my slice -> shared memory; partial normalisers -> group ----
     u64 sp = 0, sq = 0;
     pair_sums<DT, true>(prowp, qrowp, pal, qal, V, c, mcp, mcq, s0, s1, ecache, sp, sq);
-    block_sum2_u64(sp, sq, sh64);
+    block_sum2_u64(sp, sq, sh.sh64);
     if (tid == 0) {
       if (sp) atomicAdd(&ws.acc2[2 * b], sp);
       if (sq) atomicAdd(&ws.acc2[2 * b + 1], sq);
       __threadfence();
       atomicAdd(&ws.fin_done[b], 1);
-      spin_until(&ws.fin_done[b], TF_CH);
+      sh.sh_ok = spin_until(&ws.fin_done[b], TF_CH, ws.abort) ? 1 : 0;
+      dbg_stamp_max(ws, 16 + b * 8 + 4);
       const u64 Sp = __ldcg(&ws.acc2[2 * b]), Sq = __ldcg(&ws.acc2[2 * b + 1]);
-      sh_S[0] = Sp; sh_S[1] = Sq;
+      sh.sh_S[0] = Sp; sh.sh_S[1] = Sq;
       // resolved_row() reads the normalisers from acc[]: every CTA of the group stores the same values
       ws.acc[r1] = Sp;
       ws.acc[r2] = Sq;
     }
-    __syncthreads();
-    const float invp = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(sh_S[0]), 0x1p-40f));
-    const float invq = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(sh_S[1]), 0x1p-40f));
+    cta_sync();
+    if (!sh.sh_ok) return false;
+    const float invp = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(sh.sh_S[0]), 0x1p-40f));
+    const float invq = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(sh.sh_S[1]), 0x1p-40f));
     if (ch == 0 && tid == 0 && prow_i < g) {
       // the deciding position reports its exact probabilities (as the exact_rows pipeline does)
-      RowOut rp = rj.out[r1], rq = rj.out[r2];
+      RowOut rp = ldcg_rowout(&rj.out[r1]), rq = ldcg_rowout(&rj.out[r2]);
       rp.inv = invp; rq.inv = invq;
       const long long* toks = job.draft_tokens + (long long)b * g;
       const int tok = (int)min(max(toks[prow_i], 0ll), (long long)V - 1);
@@ -199,6 +198,7 @@ __global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, Hybr
     }
     // ---- phase B: residual partial sums from the cached weights ----
     const float2 inv2 = make_float2(invp, invq);
+    if (w < TF_T / 32)
     for (int seg = s0 + w; seg < s1; seg += TF_T / 32) {
       const float4* src = ecache + (size_t)(seg - s0) * 128 + lane;
       const int j0 = (seg * 32 + lane) * 8;
@@ -220,22 +220,39 @@ __global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, Hybr
     }
   }
   // ---- tail (as sample_partial_kernel): totals, then the last CTA of the group finalizes ----
-  tot = block_sum_u64(tot, sh64);
+  tot = block_sum_u64(tot, sh.sh64);
   if (GREEDY) {
     u64 key = (bidx == 0x7FFFFFFF) ? 0ull : (((u64)__float_as_uint(best)) << 32) | (u64)(0xFFFFFFFFu - (unsigned)bidx);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { const u64 t = __shfl_xor_sync(0xffffffffu, key, o); key = t > key ? t : key; }
     if (lane == 0 && key) atomicMax(&ws.best[b], key);
   }
-  __syncthreads();
+  cta_sync();
   if (tid == 0) {
     if (tot) atomicAdd(&ws.tot[b], tot);
     __threadfence();
-    sh_last = (atomicAdd(&ws.part_done[b], 1) == TF_CH - 1) ? 1 : 0;
+    sh.sh_last = (atomicAdd(&ws.part_done[b], 1) == TF_CH - 1) ? 1 : 0;
   }
-  __syncthreads();
-  if (sh_last) {
+  cta_sync();
+  if (sh.sh_last) {
     __threadfence();
-    finalize_sequence<DT>(job, ws, b, sh64, shf, shi, &s_res);
+    if (tid == 0) dbg_stamp_max(ws, 16 + b * 8 + 5);
+    finalize_sequence<DT>(job, ws, b, sh.sh64, sh.shf, sh.shi, &sh.s_res);
+    if (tid == 0) dbg_stamp_max(ws, 16 + b * 8 + 6);
   }
+  return true;
+}
+
+template <int DT, bool GREEDY>
+__global__ void __launch_bounds__(TF_T, 4) tail_fused_kernel(DecideJob job, HybridWs ws, int segs_per_cta, int TF_CH) {
+  extern __shared__ __align__(16) float4 ecache[];
+  __shared__ TailSh sh;
+  __shared__ int sh_ticket;
+  // (the ticket counter was zeroed by the memset at the head of the call, long before the plan kernel: tickets can
+  // be taken while the plan kernel is still running; its results are only read after the dependency wait)
+  if (threadIdx.x == 0) sh_ticket = atomicAdd(ws.ticket, 1);
+  grid_dependency_wait();
+  __syncthreads();
+  const int b = sh_ticket / TF_CH, ch = sh_ticket - b * TF_CH;
+  tail_item<DT, GREEDY>(job, ws, b, ch, TF_CH, segs_per_cta, ecache, sh, ws.seq_tasks[b], false, make_int4(0, 0, 0, 0), 0);
 }

@@ -80,7 +80,7 @@ __device__ __forceinline__ void sweep_range(const void* row, int V, bool aligned
 template <int DT, typename F>
 __device__ __forceinline__ void sweep(const void* row, int V, bool aligned, F f) {
   const int NV = (V + 7) >> 3;
-  const int NTB = blockDim.x;
+  const int NTB = cta_nthreads();
   int v = threadIdx.x;
   for (; v + 3 * NTB < NV; v += 4 * NTB) {
     float x0[8], x1[8], x2[8], x3[8];
@@ -1033,12 +1033,16 @@ __device__ __forceinline__ float row_prob(const RowOut& ro, const void* row, int
   return __fmul_rn(e, ro.inv);
 }
 
+// bit 63 of a u64 the megakernel exchanges between CTAs (partial sums < 2^62): set = written in this launch
+constexpr u64 WORD_VALID = 1ull << 63;
+
 // Given the per-256-element partial sums of integer weights, find the first index whose inclusive
 // prefix sum exceeds target (warp 0 scans the partials, then re-evaluates one segment).  Block-wide
 // call; returns -1 if target >= total.
 template <typename WF>
 __device__ long long locate_token(int NV, int P, const u64* part, u64 total, u64 target, WF wf, long long* s_res) {
   const int lane = threadIdx.x & 31;
+  const bool pglobal = __isGlobal(part);  // (decide_kernel keeps its partials in shared memory)
   if (threadIdx.x < 32) {
     long long res = -1;
     if (target < total) {
@@ -1048,7 +1052,7 @@ __device__ long long locate_token(int NV, int P, const u64* part, u64 total, u64
       for (int base = 0; base < P && seg < 0; base += 128) {
         u64 pv[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { const int i = base + q * 32 + lane; pv[q] = (i < P) ? part[i] : 0ull; }
+        for (int q = 0; q < 4; ++q) { const int i = base + q * 32 + lane; pv[q] = (i < P) ? ((pglobal ? __ldcg(&part[i]) : part[i]) & ~WORD_VALID) : 0ull; }  // (partials of other CTAs: L2-coherent read; the megakernel tags them valid)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           u64 incl = pv[q];
@@ -1098,9 +1102,9 @@ __device__ long long locate_token(int NV, int P, const u64* part, u64 total, u64
     }
     if (lane == 0) *s_res = res;
   }
-  __syncthreads();
+  cta_sync();
   const long long out = *s_res;
-  __syncthreads();
+  cta_sync();
   return out;
 }
 
@@ -1113,7 +1117,7 @@ __device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in,
   const int NV = (V + 7) >> 3;
   const int P = (NV + 31) >> 5;
   const int lane = threadIdx.x & 31;
-  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += blockDim.x) {  // warp-uniform
+  for (int base = (threadIdx.x >> 5) << 5; base < NV; base += cta_nthreads()) {  // warp-uniform
     const int v = base + lane;
     u64 s = 0;
     if (v < NV) {
@@ -1125,9 +1129,9 @@ __device__ long long invcdf_sweep(int V, WF wf, bool have_target, u64 target_in,
     s = warp_sum_u64(s);
     if (lane == 0) part[base >> 5] = s;
   }
-  __syncthreads();
+  cta_sync();
   u64 loc = 0;
-  for (int i = threadIdx.x; i < P; i += blockDim.x) loc += part[i];
+  for (int i = threadIdx.x; i < P; i += cta_nthreads()) loc += part[i];
   const u64 total = block_sum_u64(loc, sh64);
   total_out = total;
   const u64 target = have_target ? target_in : scale_u24(total, u24);
@@ -1144,9 +1148,9 @@ __device__ long long block_argmax(float best, int idx, float* shf, int* shi, lon
   }
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   if (lane == 0) { shf[w] = best; shi[w] = idx; }
-  __syncthreads();
+  cta_sync();
   if (threadIdx.x < 32) {
-    const int nwarp = (blockDim.x + 31) >> 5;
+    const int nwarp = (cta_nthreads() + 31) >> 5;
     best = (lane < nwarp) ? shf[lane] : -INFINITY;
     idx = (lane < nwarp) ? shi[lane] : 0x7FFFFFFF;
 #pragma unroll
@@ -1157,9 +1161,9 @@ __device__ long long block_argmax(float best, int idx, float* shf, int* shi, lon
     }
     if (lane == 0) *s_res = (idx == 0x7FFFFFFF) ? -1ll : (long long)idx;
   }
-  __syncthreads();
+  cta_sync();
   const long long out = *s_res;
-  __syncthreads();
+  cta_sync();
   return out;
 }
 
@@ -1234,6 +1238,23 @@ __device__ long long sample_residual(const void* prow, const RowOut& rp, const v
     return g;
   }
   return x;
+}
+
+// Stop-token scan over the n accepted drafts.  sampling/speculative_decoding.py:150-152 (and ngram_assisted.py:124-126)
+// take torch.nonzero(eq(ids[1,n], stop[k,1]))[0,1]: rows of the [k,n] match matrix come first, i.e. the FIRST-LISTED
+// stop token that occurs anywhere among the accepted drafts decides, at its first position.  The batched engine
+// (engine/infer_engine.py:310-312, SPECDEC_ACCEPT_BATCHED) stops at the earliest accepted position holding any end token.
+__device__ __forceinline__ int first_stop_index(const long long* toks, int n, const long long* stop, int n_stop, int flags) {
+  if (flags & SPECDEC_ACCEPT_BATCHED) {
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < n_stop; ++k)
+        if (toks[i] == stop[k]) return i;
+    return -1;
+  }
+  for (int k = 0; k < n_stop; ++k)
+    for (int i = 0; i < n; ++i)
+      if (toks[i] == stop[k]) return i;
+  return -1;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1322,10 +1343,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
       job.mask[(long long)b * g + i] = (unsigned char)s_acc[i];
       if (!s_acc[i] && n == g) n = i;
     }
-    int fs = -1;
-    for (int i = 0; i < n && fs < 0; ++i)
-      for (int k = 0; k < job.n_stop; ++k)
-        if (toks[i] == job.stop[k]) { fs = i; break; }
+    const int fs = first_stop_index(toks, n, job.stop, job.n_stop, job.flags);
     job.n_acc[b] = n;
     job.first_stop[b] = fs;
     s_n = n;
@@ -1558,23 +1576,29 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct WsLayout {
-  size_t rowout, zero, zero_bytes, tasks, status, samp, part, total;
-  int nseg_pad;
+  size_t rowout, zero, zero_bytes, zero_bytes_mega, tasks, status, samp, part, rpart, xs, dbg, total;
+  int nseg_pad, xs_stride;
 };
 static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   WsLayout w;
   const int NV = (V + 7) >> 3;
   w.nseg_pad = ((NV + 31) >> 5) + 1;
+  w.xs_stride = (w.nseg_pad - 1 + MG_MIN_SPC - 1) / MG_MIN_SPC;  // exact items per sequence at the smallest item size
   size_t o = 0;
   w.rowout = o; o = al256(o + (size_t)R * sizeof(RowOut));
-  w.zero = o;
-  o += (size_t)R * 8 + (size_t)B * 8 * 2 + (size_t)B * 8 * 2 + 64 + 64 + (size_t)B * 4 * 6;
+  w.zero = o;  // ---- zeroed at the head of every call
+  o += (size_t)R * 8 + (size_t)B * 8 * 2 + (size_t)B * 8 * 2 + 64 + 64 + (size_t)B * 4 * 7 + (size_t)MG_SM_SLOTS * 4;
   w.zero_bytes = o - w.zero;
   o = al256(o);
+  // ---- zeroed as well when the megakernel runs (its CTAs exchange self-validating words, mega.cuh)
+  w.rpart = o; o = al256(o + (size_t)R * MG_MAXU * sizeof(float2));  // per row slice (max, sum)
+  w.xs = o; o = al256(o + (size_t)B * w.xs_stride * 32);              // per exact item {Sp, Sq, greedy key, -}
+  w.part = o; o = al256(o + (size_t)B * w.nseg_pad * 8);
+  w.zero_bytes_mega = o - w.zero;
   w.tasks = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1) * 4);
   w.status = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1));
   w.samp = o; o = al256(o + (size_t)B * 4 * SAMP_N);
-  w.part = o; o = al256(o + (size_t)B * w.nseg_pad * 8);
+  w.dbg = o; o = al256(o + (size_t)(16 + B * 8 + 1024) * 8);          // megakernel: debug timeline + SM of every CTA
   w.total = o;
   return w;
 }
@@ -1593,6 +1617,16 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   h.part_done = h.exact_done + B;
   h.fin_done = h.part_done + B;
   h.decided = h.fin_done + B;
+  h.plan_done = h.decided + B;
+  h.sm_slots = h.plan_done + B;
+  h.r_ticket = h.ntasks + 11;
+  h.abort = h.ntasks + 10;   // (ntasks[0..7] / ticket[0..7]: one counter per chunk)
+  h.x_next = h.ntasks + 8;
+  h.p_next = h.ntasks + 9;
+  h.rpart = (float2*)(base + w.rpart);
+  h.xs = (u64*)(base + w.xs);
+  h.xs_stride = w.xs_stride;
+  h.dbg = nullptr;
   h.fused = 0;
   h.tasks = (int*)(base + w.tasks);
   h.status = (unsigned char*)(base + w.status);
@@ -1606,6 +1640,14 @@ static int g_chunks = 2;    // batch chunks pipelined on two streams (specdec_se
 static int g_chunk0_pct = 50;  // share of the batch in chunk 0 when chunks == 2
 static int g_p1_ctas = 3;   // row-kernel CTAs per SM while a tail kernel of the previous chunk shares the SMs
 static int g_tf_ch = TF_CH_DEFAULT;  // CTAs per sequence of tail_fused_kernel
+static int g_mega = 0;         // "mega"=1: plain modes on 16-bit TMA-eligible rows as ONE persistent cooperative launch (mega.cuh).
+                               // Off by default: measured 0.26 ms vs 0.19 ms for the three-launch pipeline at the headline shape
+                               // (139 M vs 114 M warp instructions, the exact items are latency-bound) -- see DESIGN.md 4.3
+static int g_mega_r = 2;       // R (row streaming) CTAs per SM of the megakernel; the others are X (exact) CTAs
+static int g_mega_unit = 4;    // TMA stages (16 KB) per row slice
+static int g_mega_spc = 24;    // 256-element segments per exact item (2 KB of cached weights each, <= 24)
+static int g_mega_keep_l2 = 1; // rows streamed with the normal L2 policy (the deciding pair is re-read from L2)
+static int g_mega_dbg = 0;     // record the %globaltimer timeline of the megakernel (specdec_debug_timeline)
 struct AuxStream {  // per device: the library's high-priority stream for the chunk pipeline + fork/join events
   cudaStream_t stream;
   cudaEvent_t ev_a[8], ev_b;
@@ -1795,13 +1837,82 @@ static void sub_job(const DecideJob& dj, const HybridWs& ws, int b0, int nb, int
   w.part = ws.part + (size_t)b0 * ws.nseg_pad;
 }
 
+// The plain modes on TMA-eligible 16-bit rows: one persistent cooperative launch (mega.cuh).  mega_config() returns
+// false when the shape is not eligible (the caller then takes the three-launch pipeline).
+template <int DT>
+static bool mega_config(const DecideJob& dj, int B, MegaCfg& cfg, int& grid) {
+  const RowJob& rj = dj.rj;
+  const size_t es = (DT == DT_F32) ? 4 : 2;
+  const bool ok = g_mega && DT != DT_F32 && dj.gamma > 0 && rj.top_k == 0 && !rj.use_p && !g_force_ldg && !g_no_fused_tail &&
+                  !(dj.flags & SPECDEC_NGRAM) && (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
+                  ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 && ((size_t)rj.dsb * es) % 16 == 0 &&
+                  ((size_t)rj.dsg * es) % 16 == 0;
+  if (!ok) return false;
+  static int occ_dev[MAXDEV][2];
+  int& occ = occ_dev[cur_dev()][dj.greedy ? 1 : 0];
+  if (!occ) {
+    auto kern = dj.greedy ? verify_mega_kernel<DT, true> : verify_mega_kernel<DT, false>;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, TS_THREADS, TS_SMEM) != cudaSuccess || occ < 1)
+      occ = -1;
+  }
+  if (occ < 2) return false;
+  const int per_sm = occ < 4 ? occ : 4;
+  const int r_per_sm = g_mega_r < per_sm ? g_mega_r : per_sm - 1;
+  grid = per_sm * num_sms();
+  cfg.n_r = r_per_sm * num_sms();
+  cfg.n_x = grid - cfg.n_r;
+  cfg.r_per_sm = r_per_sm;
+  const long long row_bytes = (long long)rj.V * (long long)es;
+  const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
+  cfg.unit_stages = g_mega_unit;
+  if ((nst + cfg.unit_stages - 1) / cfg.unit_stages > MG_MAXU) cfg.unit_stages = (nst + MG_MAXU - 1) / MG_MAXU;
+  cfg.U = (nst + cfg.unit_stages - 1) / cfg.unit_stages;
+  const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5);
+  cfg.spc = nseg < g_mega_spc ? nseg : g_mega_spc;
+  cfg.S = (nseg + cfg.spc - 1) / cfg.spc;
+  cfg.B = B;
+  cfg.keep_l2 = g_mega_keep_l2;
+  return grid - cfg.n_r >= 3 * cfg.S + 1;  // forward-progress condition of the item claims
+}
+template <int DT>
+static cudaError_t launch_mega(const DecideJob& dj, HybridWs ws, const MegaCfg& cfg, int grid, cudaStream_t st) {
+  auto kern = dj.greedy ? verify_mega_kernel<DT, true> : verify_mega_kernel<DT, false>;
+  ws.fused = 1;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeCooperative;
+  at[0].val.cooperative = 1;
+  cudaLaunchConfig_t lc;
+  memset(&lc, 0, sizeof(lc));
+  lc.stream = st; lc.attrs = at; lc.numAttrs = 1;
+  lc.gridDim = dim3((unsigned)grid); lc.blockDim = dim3(TS_THREADS); lc.dynamicSmemBytes = TS_SMEM;
+  return cudaLaunchKernelEx(&lc, kern, dj, ws, cfg);
+}
+
 template <int DT>
 static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* workspace, int B, cudaStream_t st) {
   const RowJob& rj = dj.rj;
   const bool masked = rj.top_k > 0 || rj.use_p;
   HybridWs ws = ws_pointers(wl, workspace, B, rj.R);
-  cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st);
+  MegaCfg mcfg;
+  int mgrid = 0;
+  const bool mega = mega_config<DT>(dj, B, mcfg, mgrid);
+  cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, mega ? wl.zero_bytes_mega : wl.zero_bytes, st);
   if (e != cudaSuccess) return e;
+  if (mega) {
+    if (g_mega_dbg) {  // timeline: minima start at ~0ull, maxima at 0
+      ws.dbg = (u64*)((char*)workspace + wl.dbg);
+      cudaMemsetAsync(ws.dbg, 0, (size_t)(16 + B * 8 + 1024) * 8, st);
+      cudaMemsetAsync(ws.dbg, 0xFF, 8, st);
+      cudaMemsetAsync(ws.dbg + 3, 0xFF, 8, st);
+      for (int b = 0; b < B; ++b) cudaMemsetAsync(ws.dbg + 16 + b * 8 + 2, 0xFF, 8, st);
+    }
+    if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+    if ((e = launch_mega<DT>(dj, ws, mcfg, mgrid, st)) != cudaSuccess) return e;
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+    return cudaGetLastError();
+  }
   // Chunks of the batch pipelined on two streams: the HBM-bound row kernel of chunk i+1 overlaps the
   // latency/issue-bound exact tail of chunk i.  Results do not depend on the split.
   int C = g_chunks;
@@ -1957,12 +2068,24 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
 
 int specdec_set_option(const char* name, int value) {
   if (!name) return SPECDEC_ERR_ARG;
+  if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
+    g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
+    g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
+    g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    return 0;
+  }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
   if (!strcmp(name, "no_overlap")) { g_chunks = value ? 1 : 2; return 0; }
   if (!strcmp(name, "chunks")) { if (value < 0 || value > 8) return SPECDEC_ERR_ARG; g_chunks = value ? value : 2; return 0; }  // 0 = default
   if (!strcmp(name, "chunk0_pct")) { if (value < 10 || value > 90) return SPECDEC_ERR_ARG; g_chunk0_pct = value; return 0; }
   if (!strcmp(name, "p1_ctas")) { if (value < 1 || value > 4) return SPECDEC_ERR_ARG; g_p1_ctas = value; return 0; }
   if (!strcmp(name, "tf_ch")) { if (value < 2 || value > 64) return SPECDEC_ERR_ARG; g_tf_ch = value; return 0; }
+  if (!strcmp(name, "mega")) { g_mega = value; return 0; }
+  if (!strcmp(name, "mega_r")) { if (value < 1 || value > 3) return SPECDEC_ERR_ARG; g_mega_r = value; return 0; }
+  if (!strcmp(name, "mega_unit")) { if (value < 1 || value > 64) return SPECDEC_ERR_ARG; g_mega_unit = value; return 0; }
+  if (!strcmp(name, "mega_spc")) { if (value < MG_MIN_SPC || value > TS_SMEM / TF_SEG_BYTES) return SPECDEC_ERR_ARG; g_mega_spc = value; return 0; }
+  if (!strcmp(name, "mega_keep_l2")) { g_mega_keep_l2 = value; return 0; }
+  if (!strcmp(name, "mega_dbg")) { g_mega_dbg = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   if (!strcmp(name, "no_hist_nucleus")) { g_no_hist_nucleus = value; return 0; }
   if (!strcmp(name, "no_tma_nucleus")) { g_no_tma_nucleus = value; return 0; }
@@ -1982,6 +2105,15 @@ int specdec_debug_stats(unsigned long long* out16, int reset) {
     e = cudaMemcpyToSymbol(g_nh_stats, z, sizeof(z));
   }
   return (int)e;
+}
+
+int specdec_debug_timeline(const void* workspace, int B, int gamma, int V, unsigned long long* host_out, int n) {
+  if (!workspace || !host_out || B <= 0) return SPECDEC_ERR_ARG;
+  const WsLayout wl = ws_layout(B, gamma, V, (long long)B * (2 * gamma + 1));
+  const int have = 16 + B * 8 + 1024;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) return (int)e;
+  return (int)cudaMemcpy(host_out, (const char*)workspace + wl.dbg, sizeof(unsigned long long) * (size_t)(n < have ? n : have), cudaMemcpyDeviceToHost);
 }
 
 int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {

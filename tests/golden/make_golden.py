@@ -25,15 +25,35 @@ KIND = {"greedy": "greedy", "multinomial": "multinomial", "temp0.7": "multinomia
         "nucleus0.9": "nucleus", "nucleus0.9_t0.7": "nucleus", "topk50_p0.9": "topk_nucleus"}
 
 
-def tables(seed, L, V, sigma=0.7, kind="peaked", dtype=torch.float32):
-    """Position-indexed target / drafter logit tables [L, V] (float32 values, optionally bf16-rounded)."""
+def tables(seed, L, V, sigma=0.7, kind="peaked", dtype=torch.float32, force=None):
+    """Position-indexed target / drafter logit tables [L, V] (float32 values, optionally bf16-rounded).
+    kind "llm": LLM-like rows (24 dominant tokens carry almost all the mass), the shape real models emit at
+    V=128256; force = "pos:token,..." puts a one-hot row at those table positions in BOTH tables."""
     g = torch.Generator().manual_seed(9000 + seed)
-    p = 2.0 * torch.randn(L, V, generator=g)
-    if kind == "peaked":
-        idx = torch.randint(V, (L, 6), generator=g)
-        p.scatter_(1, idx, 5.0 + 3.0 * torch.rand(L, 6, generator=g))
+    if kind == "llm":
+        p = 1.5 * torch.randn(L, V, generator=g)
+        idx = torch.randint(V, (L, 24), generator=g)
+        p.scatter_(1, idx, 12.0 + 8.0 * torch.rand(L, 24, generator=g))
+        sigma = 0.4
+    else:
+        p = 2.0 * torch.randn(L, V, generator=g)
+        if kind == "peaked":
+            idx = torch.randint(V, (L, 6), generator=g)
+            p.scatter_(1, idx, 5.0 + 3.0 * torch.rand(L, 6, generator=g))
     q = p + sigma * torch.randn(L, V, generator=g)
+    if force:
+        for item in force.split(","):
+            pos, tok = (int(x) for x in item.split(":"))
+            p[pos] = -20.0; p[pos, tok] = 20.0
+            q[pos] = p[pos]
     return q.to(dtype).float(), p.to(dtype).float()
+
+
+def parse_eos(v):
+    """eos field of a golden key: "-1", "7" or a "+"-separated list "33+44" (order matters, see
+    sampling/speculative_decoding.py:150-152)."""
+    v = str(v)
+    return [int(x) for x in v.split("+")] if "+" in v else int(v)
 
 
 def gen_processor_cases():
@@ -70,17 +90,28 @@ def gen_specgen_cases():
                          dtype="bf16" if i % 2 else "f32"))
     cfgs.append(dict(seed=20, V=1500, gamma=5, mode="multinomial", max_gen_len=30, skip=True, dtype="f32"))
     cfgs.append(dict(seed=21, V=1500, gamma=3, mode="topk50_p0.9", max_gen_len=25, skip=False, dtype="bf16", eos=7))
+    # two stop tokens, the SECOND-listed one accepted earlier in the window than the first-listed one: the reference
+    # truncates at the first-listed token (torch.nonzero row order, sampling/speculative_decoding.py:150-152)
+    cfgs.append(dict(seed=22, V=1200, gamma=5, mode="multinomial", max_gen_len=20, skip=False, dtype="f32", eos="33+44",
+                     force="7:44,9:33", sigma=0.0))
+    cfgs.append(dict(seed=23, V=1200, gamma=5, mode="greedy", max_gen_len=20, skip=False, dtype="f32", eos="44+33",
+                     force="7:44,9:33", sigma=0.0))
+    # the headline vocabulary (Llama-3, V=128256), LLM-like rows, bf16 values
+    cfgs.append(dict(seed=24, V=128256, gamma=4, mode="multinomial", max_gen_len=14, skip=False, dtype="bf16", kind="llm"))
+    cfgs.append(dict(seed=25, V=128256, gamma=4, mode="nucleus0.9", max_gen_len=14, skip=False, dtype="bf16", kind="llm"))
+    cfgs.append(dict(seed=26, V=128256, gamma=4, mode="topk50_p0.9", max_gen_len=14, skip=False, dtype="bf16", kind="llm"))
     for c in cfgs:
         m = MODES[c["mode"]]
         P = 6
         L = P + c["max_gen_len"] + 2
-        q, p = tables(c["seed"], L, c["V"], dtype=torch.bfloat16 if c["dtype"] == "bf16" else torch.float32)
+        q, p = tables(c["seed"], L, c["V"], dtype=torch.bfloat16 if c["dtype"] == "bf16" else torch.float32,
+                      kind=c.get("kind", "peaked"), force=c.get("force"), sigma=float(c.get("sigma", 0.7)))
         rng = np.random.RandomState(100 + c["seed"])
         su, au = rng.rand(4096).astype(np.float32), rng.rand(4096).astype(np.float32)
         prompt = rng.randint(0, c["V"], size=P).tolist()
         toks, rate, ns, na = rh.run_speculative_generate(
             prompt, q, p, KIND[c["mode"]], gamma=c["gamma"], max_gen_len=c["max_gen_len"], temperature=m["temperature"],
-            top_k=m["top_k"], top_p=m["top_p"], eos=c.get("eos", -1), skip_sample_adjustment=c["skip"], sample_u=su,
+            top_k=m["top_k"], top_p=m["top_p"], eos=parse_eos(c.get("eos", -1)), skip_sample_adjustment=c["skip"], sample_u=su,
             accept_u=au)
         key = "spec|" + "|".join(f"{k}={c[k]}" for k in sorted(c))
         out[key + "|tokens"] = np.asarray(toks, np.int64)

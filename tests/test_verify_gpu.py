@@ -221,26 +221,100 @@ def test_tma_and_ldg_row_kernels_agree(oracle_mod):
     _assert_same(o, r1)
 
 
-def test_half_batch_pipelining_does_not_change_results(oracle_mod):
-    """optional two-stream half-batch pipelining (B >= 64): results equal the single-stream path and the oracle."""
+@pytest.mark.parametrize("B,gamma,V", [(160, 3, 8192), (200, 4, 32000)])
+def test_chunk_pipelining_does_not_change_results(oracle_mod, B, gamma, V):
+    """bf16 batches of >= 128 sequences run as two chunks on two streams by default (the path bench.py times):
+    "chunks"=1 (single stream), the default (2) and 3 chunks give identical outputs, equal to the oracle."""
     import specdec_b200 as sd
     lib = sd._lib.lib()
-    case = make_case(B=70, gamma=3, V=8192, dtype="bf16", sigma=0.6, seed=41, oracle=oracle_mod)
+    case = make_case(B=B, gamma=gamma, V=V, dtype="bf16", sigma=0.6, seed=41, oracle=oracle_mod)
     args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
-    r1 = sd.fused_verify(*args, stop_tokens=[5, 77])
-    torch.cuda.synchronize()
-    assert lib.specdec_set_option(b"no_overlap", 0) == 0
-    try:
-        r2 = sd.fused_verify(*args, stop_tokens=[5, 77])
+    res = {}
+    for chunks in (0, 1, 3):  # 0 = library default
+        assert lib.specdec_set_option(b"chunks", chunks) == 0
+        res[chunks] = sd.fused_verify(*args, stop_tokens=[5, 77])
         torch.cuda.synchronize()
-    finally:
-        lib.specdec_set_option(b"no_overlap", 1)
-    for a, b in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.accept_mask, r2.accept_mask),
-                 (r1.first_stop, r2.first_stop), (r1.packed, r2.packed), (r1.p_tok, r2.p_tok), (r1.next_prob, r2.next_prob)):
-        assert torch.equal(a, b)
+    assert lib.specdec_set_option(b"chunks", 0) == 0
+    for other in (1, 3):
+        r1, r2 = res[0], res[other]
+        for a, b in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.accept_mask, r2.accept_mask),
+                     (r1.first_stop, r2.first_stop), (r1.packed, r2.packed), (r1.p_tok, r2.p_tok), (r1.next_prob, r2.next_prob)):
+            assert torch.equal(a, b)
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"],
                           stop_tokens=[5, 77])
-    _assert_same(o, r1)
+    _assert_same(o, res[0])
+
+
+def _full_size_case(B, gamma, V, mode, seed, oracle_mod, sigma=0.5, kind="randn"):
+    """bench.py-shaped inputs built on the CPU in slabs (the oracle needs them on the host anyway)."""
+    m = MODES[mode]
+    g = torch.Generator().manual_seed(9000 + seed)
+    t = torch.empty(B, gamma + 1, V, dtype=torch.bfloat16)
+    d = torch.empty(B, gamma, V, dtype=torch.bfloat16)
+    for b0 in range(0, B, 32):
+        b1 = min(B, b0 + 32)
+        tf = 3.0 * torch.randn(b1 - b0, gamma + 1, V, generator=g)
+        if kind == "peaked":
+            idx = torch.randint(V, (b1 - b0, gamma + 1, 24), generator=g)
+            tf = tf * 0.5
+            tf.scatter_(2, idx, 12.0 + 8.0 * torch.rand(b1 - b0, gamma + 1, 24, generator=g))
+        t[b0:b1] = tf.to(torch.bfloat16)
+        d[b0:b1] = (tf[:, :gamma] + sigma * torch.randn(b1 - b0, gamma, V, generator=g)).to(torch.bfloat16)
+    ud = torch.rand(B * gamma, generator=g)
+    tok, _ = oracle_mod.sample_rows(d.float().numpy().reshape(B * gamma, V), ud.numpy(), **m)
+    return dict(target=t, draft=d, draft_tokens=torch.from_numpy(tok.reshape(B, gamma)),
+                u_accept=torch.rand(B, gamma, generator=g), u_sample=torch.rand(B, generator=g))
+
+
+@pytest.mark.parametrize("mode", ["multinomial", "greedy", "topk50", "nucleus0.9"])
+def test_headline_shape_matches_oracle(oracle_mod, mode):
+    """BASELINE.json headline shape -- B=256, gamma=4, V=128256, bf16, DEFAULT library options (the exact path
+    bench.py times) -- against the oracle: accepted lengths, emitted tokens, masks bit-exact."""
+    case = _full_size_case(256, 4, 128256, mode, 1, oracle_mod)
+    o, r = _run_both(oracle_mod, case, mode)
+    _assert_same(o, r)
+    assert 0 < int(o.n_accepted.sum()) < 256 * 4
+
+
+def test_headline_shape_philox_and_repeat_calls(oracle_mod):
+    """same shape, uniforms from the in-kernel Philox stream (as bench.py runs it), several back-to-back calls on
+    the same stream (workspace reuse across calls), compared with the oracle fed the dumped uniforms."""
+    import specdec_b200 as sd
+    B, g, V = 256, 4, 128256
+    case = _full_size_case(B, g, V, "multinomial", 2, oracle_mod)
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens")]
+    rs = [sd.fused_verify(*args, None, None, seed=2025, offset=i, seq_id0=512) for i in range(4)]
+    torch.cuda.synchronize()
+    for i in (0, 3):
+        ua, us = sd.philox_uniform(2025, i, 512, B, g)
+        o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], ua.cpu(), us.cpu())
+        _assert_same(o, rs[i])
+
+
+def test_config2_shape_matches_oracle(oracle_mod):
+    """BASELINE.json configs[2] shape: batch 64, gamma=4, nucleus p=0.9, V=128256 bf16; LLM-like (peaked) rows and
+    the flat rows random-init models emit."""
+    for kind, seed in (("peaked", 3), ("randn", 4)):
+        case = _full_size_case(64, 4, 128256, "nucleus0.9", seed, oracle_mod, kind=kind)
+        o, r = _run_both(oracle_mod, case, "nucleus0.9")
+        _assert_same(o, r)
+
+
+@pytest.mark.parametrize("mode", ["greedy", "multinomial"])
+def test_config3_shape_ngram_matches_oracle(oracle_mod, mode):
+    """BASELINE.json configs[3] shape: n-gram-assisted verify, batch 128, gamma=6, V=128256 bf16."""
+    B, g, V = 128, 6, 128256
+    case = _full_size_case(B, g, V, mode, 5, oracle_mod, sigma=0.0, kind="peaked")
+    m = MODES[mode]
+    tok, _ = oracle_mod.sample_rows(case["target"][:, :g].float().numpy().reshape(B * g, V),
+                                    case["u_accept"].numpy().reshape(-1), **m)
+    toks = torch.from_numpy(tok.reshape(B, g)).clone()
+    toks[::2, 3] = 17
+    toks[1::5, 0] = 9
+    case["draft_tokens"] = toks
+    o, r = _run_both(oracle_mod, case, mode, flags=F_NGRAM)
+    _assert_same(o, r, ngram=True)
+    assert o.n_accepted.max() == g and o.n_accepted.min() == 0
 
 
 @pytest.mark.parametrize("dtype", ["bf16", "f32"])
@@ -553,3 +627,41 @@ def test_ngram_greedy_tma_argmax_edge_rows(oracle_mod, dtype):
     _assert_same(o, r2, ngram=True)
     assert int(r.next_token[2]) in (1234,) or int(o.n_accepted[2]) < g  # (bonus row of sequence 2: first tied index)
     assert torch.equal(r.n_accepted, r2.n_accepted) and torch.equal(r.next_token, r2.next_token)
+
+
+# ---- the persistent single-launch path (csrc/mega.cuh, option "mega"=1; off by default) ----
+@pytest.mark.parametrize("B,gamma,V,dtype,greedy,flags", [
+    (256, 4, 128256, "bf16", False, 0), (64, 4, 128256, "bf16", True, 0), (7, 3, 32000, "f16", False, F_SKIP),
+    (33, 6, 50264, "bf16", False, F_BATCHED | F_NO_BONUS | F_FALLBACK), (1, 8, 128256, "bf16", False, 0),
+    (300, 2, 4096, "bf16", False, F_NO_BONUS)])
+def test_megakernel_matches_oracle_and_three_launch_pipeline(oracle_mod, B, gamma, V, dtype, greedy, flags):
+    """one cooperative launch (row-slice streaming CTAs + exact-item CTAs exchanging self-validating words): identical
+    outputs to the three-launch pipeline and to the oracle, incl. accept tests inside the fast path's margin."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    case = make_case(B=B, gamma=gamma, V=V, dtype=dtype, sigma=0.5, seed=91 + B, oracle=oracle_mod)
+    o0 = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"])
+    ua = case["u_accept"].clone()
+    ratio = torch.from_numpy(o0.p_tok / np.maximum(o0.q_tok, 1e-30)).float()
+    rng = np.random.RandomState(5)
+    for b in range(0, B, 3):  # u on / next to the accept boundary: the in-kernel exact route for ambiguous positions
+        i = int(rng.randint(gamma))
+        if 0.0 < float(ratio[b, i]) < 1.0:
+            ua[b, i] = float(ratio[b, i]) * (1.0 + (int(rng.randint(3)) - 1) * 1e-4)
+    case["u_accept"] = ua
+    tgt = case["target"][:, :-1] if (flags & F_NO_BONUS) else case["target"]
+    kw = dict(greedy=greedy, flags=flags, stop_tokens=[int(case["draft_tokens"][0, 0])])
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], ua, case["u_sample"],
+                          greedy=greedy, flags=flags, stop_tokens=kw["stop_tokens"])
+    args = [tgt.cuda(), case["draft"].cuda(), case["draft_tokens"].cuda(), ua.cuda(), case["u_sample"].cuda()]
+    r0 = sd.fused_verify(*args, **kw)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"mega", 1) == 0
+    rs = [sd.fused_verify(*args, **kw) for _ in range(3)]  # (workspace reuse across back-to-back launches)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"mega", 0) == 0
+    for r1 in rs:
+        _assert_same(o, r1)
+        for a, b_ in ((r0.n_accepted, r1.n_accepted), (r0.next_token, r1.next_token), (r0.accept_mask, r1.accept_mask),
+                      (r0.packed, r1.packed), (r0.next_prob, r1.next_prob), (r0.first_stop, r1.first_stop)):
+            assert torch.equal(a, b_)
