@@ -380,19 +380,23 @@ def run_ours(args):
             kv = [torch.zeros(Bk, Hk, Sk, Dk, dtype=torch.bfloat16, device=dev) for _ in range(2 * Lk)]
             lens = torch.full((Bk,), Sk, dtype=torch.int32, device=dev)
             disc = torch.randint(1, g + 2, (Bk,), device=dev, dtype=torch.int32)
-            sd.prune_kv(kv, lens, disc)
-            torch.cuda.synchronize()
+            cache = sd.StaticKVCache(kv, lens)
             reps = 20
-            e0.record()
-            for i in range(reps):
-                lens.fill_(Sk)
-                sd.prune_kv(kv, lens, disc)
-            e1.record()
-            torch.cuda.synchronize()
-            msk = e0.elapsed_time(e1) / reps
-            zbytes = int(disc.sum()) * Hk * Dk * 2 * 2 * Lk
-            sweep["prune_kv"] = {"ms_per_call": msk, "bytes_zeroed": zbytes, "note": f"{2*Lk} tensors [64,8,2048,128] bf16, per-sequence discard 1..{g+1}"}
-            del kv
+            for zf in (False, True):
+                cache.rollback(disc, zero_fill=zf)
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(reps):
+                    cache.seq_lens.fill_(Sk)
+                    cache.rollback(disc, zero_fill=zf)
+                e1.record()
+                torch.cuda.synchronize()
+                msk = e0.elapsed_time(e1) / reps
+                zbytes = int(disc.sum()) * Hk * Dk * 2 * 2 * Lk
+                sweep["prune_kv" + ("_zero_fill" if zf else "")] = {
+                    "ms_per_call": msk, "bytes_zeroed": zbytes if zf else 0,
+                    "note": f"{2*Lk} tensors [64,8,2048,128] bf16, per-sequence discard 1..{g+1} (incl. the lens.fill_ launch)"}
+            del kv, cache
             # n-gram tables: per-sequence tables, B=128 sequences, prompt 256 tokens, gamma=6 chained lookups
             Bn, Ln = 128, 256
             st = sd.NGramStorage(4, V, n_tables=Bn, grams_per_table=4096, counts_per_table=8192, device=dev)

@@ -149,8 +149,10 @@ SPECDEC_API int specdec_philox_uniform(uint64_t seed, uint64_t offset, int64_t s
  * Per-sequence KV rollback on a static cache: prune_cache / prune_tuple_cache
  * (utils/caching.py:6-55; call sites sampling/speculative_decoding.py:163-165) generalised to a
  * different discard count per sequence.  tensor_ptrs: DEVICE array of n_tensors device pointers,
- * each a [B,H,S_max,D] tensor of elem_bytes-wide elements; seq_lens[B] in/out; the discarded
- * positions are zero-filled when zero_fill!=0 (so the valid prefix equals the reference's view).
+ * each a [B,H,S_max,D] tensor of elem_bytes-wide elements; seq_lens[B] in/out.  The length vector IS the
+ * rollback (the valid prefix [0, seq_lens[b]) equals the reference's view): with zero_fill == 0 the tensors are
+ * not touched (tensor_ptrs may be NULL, n_tensors 0) and the call is one ~3 us launch; zero_fill != 0 also clears
+ * the discarded positions (one CTA per (tensor, sequence), 16-byte stores).
  */
 SPECDEC_API int specdec_prune_kv(void* const* tensor_ptrs, int n_tensors, int B, int H, int64_t S_max, int64_t D,
                      int elem_bytes, int32_t* seq_lens, const int32_t* discard, int zero_fill,

@@ -69,12 +69,17 @@ class StaticKVCache:
     def __init__(self, tensors: Sequence[Tensor], seq_lens: Tensor):
         self.tensors: List[Tensor] = list(tensors)
         self.seq_lens = seq_lens.to(torch.int32).contiguous()
+        self._ptrs = None  # device table of the tensors' addresses, built on the first zero-filling rollback
 
-    def rollback(self, discard: Union[int, Tensor], zero_fill: bool = True) -> "StaticKVCache":
+    def rollback(self, discard: Union[int, Tensor], zero_fill: bool = False) -> "StaticKVCache":
+        """Drops the last discard[b] positions of sequence b.  The length vector IS the rollback (one ~3 us launch);
+        zero_fill=True additionally clears the discarded positions."""
         B = self.seq_lens.shape[0]
         if not isinstance(discard, Tensor):
             discard = torch.full((B,), int(discard), dtype=torch.int32, device=self.seq_lens.device)
-        ops.prune_kv(self.tensors, self.seq_lens, discard, zero_fill)
+        if zero_fill and self._ptrs is None:
+            self._ptrs = ops.kv_pointer_table(self.tensors)
+        ops.prune_kv(self.tensors, self.seq_lens, discard, zero_fill, self._ptrs if zero_fill else None)
         return self
 
     def as_tuple_views(self, b: int):

@@ -252,10 +252,13 @@ __device__ __forceinline__ void cta_sync() {
 }
 
 // ---- block-wide reductions (up to 32 warps); `sh` = 33-entry scratch ----
+// Exact (mod 2^64) warp sum of u64 values: three independent hardware integer reductions (REDUX) over 22 / 22 / 20-bit
+// pieces instead of five dependent 64-bit shuffle-add rounds -- a third of the latency, half the instructions.
 __device__ __forceinline__ u64 warp_sum_u64(u64 v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
+  const unsigned a = (unsigned)v & 0x3FFFFFu, b = (unsigned)(v >> 22) & 0x3FFFFFu, c = (unsigned)(v >> 44);
+  const unsigned sa = __reduce_add_sync(0xffffffffu, a), sb = __reduce_add_sync(0xffffffffu, b),
+                 sc = __reduce_add_sync(0xffffffffu, c);
+  return (u64)sa + ((u64)sb << 22) + ((u64)sc << 44);
 }
 __device__ __forceinline__ float warp_max_f(float v) {
 #pragma unroll

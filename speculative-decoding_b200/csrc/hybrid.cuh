@@ -690,6 +690,7 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int mode = ws.samp[b * SAMP_N + 1], prow = ws.samp[b * SAMP_N + 2];
   if (mode == 0) return;
+  if (MASKED && ws.part_done[b] >= CH) return;  // drawn from the kept-token lists by sample_lists_kernel
   const long long r1 = (long long)b * rps + prow;
   const void* prowp = row_ptr<DT>(rj, r1);
   const RowOut rp = resolved_row(rj, ws, r1);
@@ -732,6 +733,168 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
   if (sh_last) {
     __threadfence();
     finalize_sequence<DT>(job, ws, b, sh64, shf, shi, &s_res);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// sample_lists_kernel (masked modes): one WARP per sequence.  When the rows the next token is drawn from carry a
+// kept-token list (RowJob::klist: top-k, top-k + top-p, small nuclei -- at most KL_MAX tokens), the draw needs no
+// sweep over the vocabulary: the residual max(0, P - Q) lives on the target row's kept tokens.  The same integers
+// as sample_partial_kernel + finalize_sequence are summed (fix60 residuals / fix40 weights in index order), so the
+// token is bit-identical.  Sequences without lists are left to sample_partial_kernel (ws.part_done[b] stays 0;
+// handled sequences set it to CH so that kernel's CTAs return at once).
+// ---------------------------------------------------------------------------------------------
+constexpr int SL_WARPS = 8;
+template <int DT>
+__global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob job, HybridWs ws, int B) {
+  __shared__ int s_j[SL_WARPS][KL_MAX];
+  __shared__ float s_p[SL_WARPS][KL_MAX];
+  __shared__ u64 s_w[SL_WARPS][KL_MAX];
+  __shared__ int s_qj[SL_WARPS][KL_MAX];
+  __shared__ float s_qz[SL_WARPS][KL_MAX];
+  grid_dependency_wait();
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * SL_WARPS + wib;
+  if (b >= B) return;
+  const RowJob& rj = job.rj;
+  const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
+  const int n = ws.samp[b * SAMP_N + 0], mode = ws.samp[b * SAMP_N + 1], prow = ws.samp[b * SAMP_N + 2];
+  if (mode == 0) { if (lane == 0) ws.part_done[b] = CH; return; }  // decide_sequence wrote the outputs
+  const long long r1 = (long long)b * rps + prow, r2 = (long long)b * rps + rj.nT + prow;
+  const RowOut rp = rj.out[r1];
+  RowOut rq = rp;
+  if (mode == 2) rq = rj.out[r2];
+  const int cp = (rp.flags >> 8) & 0xFF, cq = (mode == 2) ? ((rq.flags >> 8) & 0xFF) : 1;
+  if (cp == 0 || cq == 0) return;  // no list: sample_partial_kernel does this sequence
+  const float c = rj.c;
+  const bool greedy = job.greedy != 0;
+  const float us = job.u_sample ? job.u_sample[b]
+                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
+  int* sj = s_j[wib]; float* sp = s_p[wib]; u64* sw = s_w[wib]; int* sqj = s_qj[wib]; float* sqz = s_qz[wib];
+  // ---- load the lists; the target row's list sorted by token index (rank sort: KL_MAX^2 / 32 comparisons per lane)
+  const int2* lp = rj.klist + r1 * KL_MAX;
+  int2 e[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) e[h] = (lane + 32 * h < cp) ? lp[lane + 32 * h] : make_int2(0, 0x7FFFFFFF);
+  if (mode == 2) {
+    const int2* lq = rj.klist + r2 * KL_MAX;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (lane + 32 * h < cq) { const int2 q = lq[lane + 32 * h]; sqj[lane + 32 * h] = q.y; sqz[lane + 32 * h] = __int_as_float(q.x); }
+  }
+#pragma unroll
+  for (int h = 0; h < 2; ++h) sj[lane + 32 * h] = e[h].y;
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    if (lane + 32 * h < cp) {
+      int rank = 0;
+      for (int i = 0; i < cp; ++i) rank += (sj[i] < e[h].y) ? 1 : 0;
+      // probabilities exactly as row_prob(): kept tokens only, canonical weight times the exact 1/S
+      const float zp = __int_as_float(e[h].x);
+      const float P = __fmul_rn(cweight(zp, c, rp.mc), rp.inv);
+      float val = P;  // mode 1: weight fix40(e); kept for the greedy arg-max as e (not e * inv) below
+      u64 w;
+      if (mode == 2) {
+        float Q = 0.0f;
+        for (int i = 0; i < cq; ++i)
+          if (sqj[i] == e[h].y) Q = __fmul_rn(cweight(sqz[i], c, rq.mc), rq.inv);
+        val = fmaxf(__fsub_rn(P, Q), 0.0f);
+        w = fix60(val);
+      } else {
+        val = cweight(zp, c, rp.mc);
+        w = fix40(val);
+      }
+      e[h].x = rank;  // (reuse: destination slot)
+      s_w[wib][rank] = w;
+      sp[rank] = val;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (lane + 32 * h < cp) sj[e[h].x] = e[h].y;  // token ids in index order (ranks are a permutation: indices are distinct)
+  __syncwarp();
+  // ---- totals, fallback rule, draw
+  u64 w0 = (2 * lane < cp) ? sw[2 * lane] : 0ull, w1 = (2 * lane + 1 < cp) ? sw[2 * lane + 1] : 0ull;
+  u64 incl = w0 + w1;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  u64 total = __shfl_sync(0xffffffffu, incl, 31);
+  const u64 rmin = (job.flags & SPECDEC_RESID_FALLBACK) ? 1152921ull : 0ull;
+  bool from_p = (mode == 1);
+  if (mode == 2 && total <= rmin) {
+    // residual mass (numerically) zero: sample the target row itself (engine/infer_engine.py:319-321)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * lane + h;
+      if (i < cp) {
+        const float zp = load1<DT>(row_ptr<DT>(rj, r1), sj[i]);
+        const float ev = cweight(zp, c, rp.mc);
+        sp[i] = ev; sw[i] = fix40(ev);
+      }
+    }
+    __syncwarp();
+    w0 = (2 * lane < cp) ? sw[2 * lane] : 0ull; w1 = (2 * lane + 1 < cp) ? sw[2 * lane + 1] : 0ull;
+    incl = w0 + w1;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const u64 t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    total = __shfl_sync(0xffffffffu, incl, 31);
+    from_p = true;
+  }
+  long long x = -1;
+  if (greedy) {  // largest value, first index on ties (values > 0 only, as the sweep kernels: key == 0 -> token 0)
+    float bv = -1.0f; int bi = 0x7FFFFFFF;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = 2 * lane + h;
+      if (i < cp && sp[i] > bv && (from_p || sp[i] > 0.0f)) { bv = sp[i]; bi = sj[i]; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+    }
+    x = (bi == 0x7FFFFFFF) ? 0ll : (long long)bi;
+  } else {
+    const u64 target = scale_u24(total, u24_of(us));
+    // first index whose inclusive prefix sum exceeds target
+    const u64 excl = incl - (w0 + w1);
+    int hit = -1;
+    if (target < total) {
+      if (excl + w0 > target) hit = 2 * lane;
+      else if (excl + w0 + w1 > target) hit = 2 * lane + 1;
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, hit >= 0);
+    if (bal) {
+      const int owner = __ffs(bal) - 1;
+      hit = __shfl_sync(0xffffffffu, hit, owner);
+      x = (long long)sj[hit];
+    }
+  }
+  if (lane == 0) {
+    job.next_tok[b] = x;
+    if (job.next_prob) {
+      float np = 0.0f;
+      if (from_p && x >= 0) np = row_prob<DT>(rp, row_ptr<DT>(rj, r1), (int)x, c);
+      job.next_prob[b] = np;
+    }
+    if (job.packed) {
+      const long long* toks = job.draft_tokens + (long long)b * g;
+      int* pk = job.packed + (long long)b * (g + 2);
+      pk[0] = n;
+      for (int i = 0; i < g + 1; ++i) pk[1 + i] = -1;
+      for (int i = 0; i < n; ++i) pk[1 + i] = (int)toks[i];
+      pk[1 + n] = (int)x;
+    }
+    ws.part_done[b] = CH;  // handled: sample_partial_kernel's CTAs of this sequence return at once
   }
 }
 

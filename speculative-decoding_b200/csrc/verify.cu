@@ -44,7 +44,10 @@ struct RowJob {
   RowOut* out;
   int skip_resolved;  // rowstats_kernel: skip rows whose RowOut is already flagged exact
   int pre_stats;      // nucleus_fast_kernel: max / MUFU mass / candidate threshold come from rowfast_tma_kernel<DT, 1>
+  int2* klist;        // nullable: [R][KL_MAX] (logit bits, index) of the kept tokens of rows whose kept set is small;
+                      // the count sits in RowOut.flags bits 8..15 (0 = no list).  Feeds sample_lists_kernel.
 };
+constexpr int KL_MAX = 64;
 
 template <int DT>
 __device__ __forceinline__ const void* row_ptr(const RowJob& job, long long r) {
@@ -303,7 +306,7 @@ template <bool BLK>
 __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw, int n, int V, int top_k, int use_p,
                                  u64 tpq, u64 S1_full, u64 G_off, u64 S_above, float c, float mc, float c1, float mc1,
                                  float& cut_out, int& jcut_out, u64& Sfix_out, u64 thr_lo = 0, u64 thr_hi = 0,
-                                 int* ambiguous = nullptr) {
+                                 int* ambiguous = nullptr, int* m_out = nullptr) {
   const int lane = threadIdx.x & 31;
   const unsigned k0 = fkey(cz[0]);
   unsigned vary = 0;
@@ -403,6 +406,24 @@ __device__ void select_cut_group(const Grp<BLK>& gp, float* cz, int* cj, u64* cw
   Sfix_out = S_above + gp.sum(loc);
   cut_out = fkey_inv(cutkey);
   jcut_out = jcut;
+  if (m_out) *m_out = m;  // cz / cj [0, m) = the candidates that survived top-k (all of them without top-k)
+}
+
+// Warp-collective: the kept tokens among candidates [0, m) -> dst (unordered); returns their number, 0 if more than KL_MAX.
+__device__ __forceinline__ int write_kept_list(const float* cz, const int* cj, int m, float cut, int jcut, int2* dst) {
+  const int lane = threadIdx.x & 31;
+  int cnt = 0;
+  for (int base = 0; base < m; base += 32) {
+    const int i = base + lane;
+    const float z = (i < m) ? cz[i] : 0.0f;
+    const int j = (i < m) ? cj[i] : 0;
+    const bool keep = (i < m) && (z > cut || (z == cut && j <= jcut));
+    const unsigned bal = __ballot_sync(0xffffffffu, keep);
+    const int pos = cnt + __popc(bal & ((1u << lane) - 1u));
+    if (keep && pos < KL_MAX) dst[pos] = make_int2(__float_as_int(z), j);
+    cnt += __popc(bal);
+  }
+  return cnt <= KL_MAX ? cnt : 0;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -427,7 +448,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
   const float c = job.c;
   constexpr bool masked = HK || HP;
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
-    if (HP && !HK && job.skip_resolved && (job.out[r].flags & 1)) continue;  // done by nucleus_fast_kernel
+    if (job.skip_resolved && (job.out[r].flags & 1)) continue;  // done by rowsel_tma_kernel / nucleus_fast_kernel (block-uniform)
     const void* row = row_ptr<DT>(job, r);
     const bool aligned = (((size_t)row) & 15) == 0;
     // sweep 1: row max (+ per-thread maxima, reused as candidate thresholds)
@@ -439,7 +460,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
     const float m = block_max_f(tmax, shf);
     const float mc = __fmul_rn(m, c);
     float cut = -INFINITY;
-    int jcut = V;
+    int jcut = V, kcnt = 0;
     u64 Sfix = 0;
     if (!masked) {
       u64 s = 0;
@@ -611,12 +632,16 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
       if (L >= 0 && n <= WARP_SELECT_MAX) {
         if (threadIdx.x < 32) {
           const Grp<false> gp{sh64, shu};
+          int mval = 0, kc = 0;
           select_cut_group<false>(gp, cz, cj, cw, n, V, job.top_k, job.use_p, job.tpq, S1, band_G, S_above, c, mc, c1, mc1,
-                                  cut, jcut, Sfix);
-          if (threadIdx.x == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; }
+                                  cut, jcut, Sfix, 0, 0, nullptr, &mval);
+          // with top-k the candidates are all elements above a threshold, i.e. a superset of the kept set: small kept
+          // sets are handed to sample_lists_kernel as a list, which then never sweeps the row again
+          if (HK && job.klist) kc = write_kept_list(cz, cj, mval, cut, jcut, job.klist + r * KL_MAX);
+          if (threadIdx.x == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; s_count = kc; }
         }
         __syncthreads();
-        cut = s_cut; jcut = s_jcut; Sfix = s_Sfix;
+        cut = s_cut; jcut = s_jcut; Sfix = s_Sfix; kcnt = s_count;
         __syncthreads();
       } else if (L >= 0 && job.top_k == 0) {
         const Grp<true> gp{sh64, shu};
@@ -640,7 +665,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
       o.m = m; o.mc = mc;
       const float S32 = __fmul_rn(__ull2float_rn(Sfix), 0x1p-40f);
       o.inv = __fdiv_rn(1.0f, S32);
-      o.cut = cut; o.jcut = jcut; o.flags = 1; o.Sfix = Sfix;
+      o.cut = cut; o.jcut = jcut; o.flags = 1 | (kcnt << 8); o.Sfix = Sfix;
       job.out[r] = o;
     }
   }
@@ -662,7 +687,7 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
   __shared__ u64 sh64[33];
   __shared__ float shf[33];
   __shared__ unsigned shu[33];
-  __shared__ int s_count, s_amb;
+  __shared__ int s_count, s_amb, s_kc;
   __shared__ float s_cut;
   __shared__ int s_jcut;
   __shared__ u64 s_Sfix;
@@ -750,7 +775,9 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
         float cut; int jcut; u64 Sfix; int amb = 1;
         select_cut_group<false>(gp, cz, cj, cw, n, V, 0, 1, job.tpq, 0ull, 0ull, 0ull, c, mc, c1, mc1, cut, jcut, Sfix,
                                 thr_lo, thr_hi, &amb);
-        if (lane == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; s_amb = amb; }
+        int kc = 0;  // (unambiguous: the candidates hold the whole nucleus)
+        if (!amb && job.klist) kc = write_kept_list(cz, cj, n, cut, jcut, job.klist + r * KL_MAX);
+        if (lane == 0) { s_cut = cut; s_jcut = jcut; s_Sfix = Sfix; s_amb = amb; s_kc = kc; }
       }
       __syncthreads();
       ok = (s_amb == 0);
@@ -760,7 +787,7 @@ __global__ void __launch_bounds__(RS_NT, 2) nucleus_fast_kernel(RowJob job) {
       o.m = m; o.mc = mc; o.cut = -INFINITY; o.jcut = V; o.flags = 0; o.Sfix = 0;
       o.inv = S1f;  // unresolved rows: the MUFU T=1 mass (relative to the max) for nucleus_hist_kernel
       if (ok) {
-        o.cut = s_cut; o.jcut = s_jcut; o.Sfix = s_Sfix; o.flags = 1;
+        o.cut = s_cut; o.jcut = s_jcut; o.Sfix = s_Sfix; o.flags = 1 | (s_kc << 8);
         o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(s_Sfix), 0x1p-40f));
       }
       job.out[r] = o;
@@ -1392,6 +1419,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
 }
 
 #include "hybrid.cuh"
+#include "rowsel_tma.cuh"
 
 // ---------------------------------------------------------------------------------------------
 // probabilities materialised (LogitsProcessor.__call__), sample() on given probs, philox dump
@@ -1485,6 +1513,7 @@ static bool pdl_enabled(cudaStream_t st) {
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
 }
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
+static int g_no_klist = 0;       // test hook: specdec_set_option("no_klist", 1) => masked modes always draw by a sweep over the row
 // per-device caches (function attributes are per device; one process may drive several GPUs)
 constexpr int MAXDEV = 32;
 static int cur_dev() {
@@ -1519,6 +1548,7 @@ static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long t
   rj.out = (RowOut*)workspace;
   rj.skip_resolved = 0;
   rj.pre_stats = 0;
+  rj.klist = nullptr;
   return 0;
 }
 
@@ -1527,6 +1557,34 @@ static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long t
 template <int DT>
 static bool nucleus_prepass_tma(const RowJob& rj, cudaStream_t st);
 
+static int g_rowsel_probe = 0;  // timing probe: the selector warp skips the selection (rows fall through)
+static int g_no_rowsel = 0;  // test hook: specdec_set_option("no_rowsel", 1) => masked modes without the streamed selection kernel
+
+// masked modes on TMA-eligible 16-bit rows: rowsel_tma_kernel resolves the rows at HBM speed; false = not eligible
+template <int DT, bool HK, bool HP>
+static bool launch_rowsel(const RowJob& rj, cudaStream_t st) {
+  if (DT == DT_F32) return false;
+  const size_t es = 2;
+  const bool ok = !g_no_rowsel && !g_no_fast_nucleus && !g_force_ldg && rj.R > 0 && (!HK || rj.top_k <= RS2_CONSUMERS) &&
+                  (((size_t)rj.tgt | (size_t)rj.drf) & 15) == 0 && ((size_t)rj.V * es) % 16 == 0 &&
+                  ((size_t)rj.tsb * es) % 16 == 0 && ((size_t)rj.tsg * es) % 16 == 0 && ((size_t)rj.dsb * es) % 16 == 0 &&
+                  ((size_t)rj.dsg * es) % 16 == 0;
+  if (!ok) return false;
+  static int occ_dev[MAXDEV];
+  int& occ = occ_dev[cur_dev()];
+  if (!occ) {
+    if (cudaFuncSetAttribute(rowsel_tma_kernel<DT, HK, HP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RS2_SMEM) != cudaSuccess ||
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, rowsel_tma_kernel<DT, HK, HP>, RS2_THREADS, RS2_SMEM) != cudaSuccess || occ < 1)
+      occ = -1;
+  }
+  if (occ < 1) return false;
+  const long long cap = (long long)(occ < 2 ? occ : 2) * num_sms();
+  RowJob rjp = rj;
+  rjp.pre_stats = g_rowsel_probe;
+  rowsel_tma_kernel<DT, HK, HP><<<(unsigned)(rj.R < cap ? rj.R : cap), RS2_THREADS, RS2_SMEM, st>>>(rjp);
+  return cudaGetLastError() == cudaSuccess;
+}
+
 template <int DT>
 static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   if (rj.R == 0) return cudaSuccess;
@@ -1534,49 +1592,50 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   const size_t smem = masked ? CAND_SMEM : 0;
   const long long cap = 2LL * num_sms();
   const int grid = (int)(rj.R < cap ? rj.R : cap);
-#define RS_LAUNCH(HKv, HPv)                                                                                         \
+#define RS_LAUNCH(HKv, HPv, JOB)                                                                                    \
   do {                                                                                                              \
     if (masked) {                                                                                                   \
       cudaError_t e = cudaFuncSetAttribute(rowstats_kernel<DT, HKv, HPv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                            (int)smem);                                                              \
       if (e != cudaSuccess) return e;                                                                               \
     }                                                                                                               \
-    rowstats_kernel<DT, HKv, HPv><<<grid, RS_NT, smem, st>>>(rj);                                                    \
+    rowstats_kernel<DT, HKv, HPv><<<grid, RS_NT, smem, st>>>(JOB);                                                   \
   } while (0)
-  if (rj.top_k > 0 && rj.use_p) RS_LAUNCH(true, true);
-  else if (rj.top_k > 0) RS_LAUNCH(true, false);
-  else if (rj.use_p) {
+  if (!masked) { RS_LAUNCH(false, false, rj); return cudaGetLastError(); }
+  // Fast route: rowsel_tma_kernel (one streamed pass + gather of the hot slices + exact selection by a selector warp);
+  // the rows it leaves unresolved go to the exact kernels below, which skip every row already flagged.
+  RowJob left = rj;
+  if (rj.top_k > 0 && rj.use_p) {
+    if (launch_rowsel<DT, true, true>(rj, st)) left.skip_resolved = 1;
+    RS_LAUNCH(true, true, left);
+  } else if (rj.top_k > 0) {
+    if (launch_rowsel<DT, true, false>(rj, st)) left.skip_resolved = 1;
+    RS_LAUNCH(true, false, left);
+  } else {
     if (!g_no_fast_nucleus) {
-      cudaError_t e = cudaFuncSetAttribute(nucleus_fast_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      RowJob rj1 = rj;
-      if (nucleus_prepass_tma<DT>(rj, st)) rj1.pre_stats = 1;  // max / MUFU mass / candidate threshold at HBM speed
-      nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj1);
+      cudaError_t e;
+      if (!launch_rowsel<DT, false, true>(rj, st)) {
+        if ((e = cudaFuncSetAttribute(nucleus_fast_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        RowJob rj1 = rj;
+        if (nucleus_prepass_tma<DT>(rj, st)) rj1.pre_stats = 1;  // max / MUFU mass / candidate threshold at HBM speed
+        nucleus_fast_kernel<DT><<<grid, RS_NT, smem, st>>>(rj1);
+      }
       if (!g_no_hist_nucleus) {  // flat rows: radix-select by private histograms, cost independent of the nucleus size
-        cudaError_t e3 = cudaFuncSetAttribute(nucleus_hist_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NH_SMEM);
-        if (e3 != cudaSuccess) return e3;
+        if ((e = cudaFuncSetAttribute(nucleus_hist_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)NH_SMEM)) != cudaSuccess) return e;
         const int gh = (int)(rj.R < (long long)num_sms() ? rj.R : (long long)num_sms());
         nucleus_hist_kernel<DT><<<gh, NH_T, NH_SMEM, st>>>(rj);
       }
-      RowJob rj2 = rj;
-      rj2.skip_resolved = 1;
-      {
-        cudaError_t e2 = cudaFuncSetAttribute(rowstats_kernel<DT, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e2 != cudaSuccess) return e2;
-        rowstats_kernel<DT, false, true><<<grid, RS_NT, smem, st>>>(rj2);
-      }
-    } else {
-      RS_LAUNCH(false, true);
+      left.skip_resolved = 1;
     }
+    RS_LAUNCH(false, true, left);
   }
-  else RS_LAUNCH(false, false);
 #undef RS_LAUNCH
   return cudaGetLastError();
 }
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 struct WsLayout {
-  size_t rowout, zero, zero_bytes, zero_bytes_mega, tasks, status, samp, part, rpart, xs, dbg, total;
+  size_t rowout, zero, zero_bytes, zero_bytes_mega, tasks, status, samp, part, rpart, xs, dbg, klist, total;
   int nseg_pad, xs_stride;
 };
 static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
@@ -1599,6 +1658,7 @@ static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   w.status = o; o = al256(o + (size_t)B * (gamma > 0 ? gamma : 1));
   w.samp = o; o = al256(o + (size_t)B * 4 * SAMP_N);
   w.dbg = o; o = al256(o + (size_t)(16 + B * 8 + 1024) * 8);          // megakernel: debug timeline + SM of every CTA
+  w.klist = o; o = al256(o + (size_t)R * KL_MAX * sizeof(int2));      // masked modes: kept-token lists of small kept sets
   w.total = o;
   return w;
 }
@@ -1799,6 +1859,11 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   cfg.gridDim = dim3((unsigned)B, CH); cfg.blockDim = dim3(PT);
   if (!masked && dj.gamma > 0)  // tasks are looped over
     if ((e = cudaLaunchKernelEx(&cfg, exact_rows_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  if (masked && rj.klist) {  // sequences whose deciding rows carry kept-token lists are drawn without a sweep
+    cfg.gridDim = dim3((unsigned)((B + SL_WARPS - 1) / SL_WARPS)); cfg.blockDim = dim3(SL_WARPS * 32);
+    if ((e = cudaLaunchKernelEx(&cfg, sample_lists_kernel<DT>, dj, ws, B)) != cudaSuccess) return e;
+    cfg.gridDim = dim3((unsigned)B, CH); cfg.blockDim = dim3(PT);
+  }
   auto samp = masked ? (dj.greedy ? sample_partial_kernel<DT, true, true> : sample_partial_kernel<DT, true, false>)
                      : (dj.greedy ? sample_partial_kernel<DT, false, true> : sample_partial_kernel<DT, false, false>);
   if ((e = cudaLaunchKernelEx(&cfg, samp, dj, ws)) != cudaSuccess) return e;
@@ -2022,6 +2087,7 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
   int rc = fill_rowjob(dj.rj, target_logits, draft_logits, stride_tb, stride_tg, stride_db, stride_dg, nT, nD, V,
                        temperature, top_k, top_p, R, workspace, workspace_bytes);
   if (rc) return rc;
+  if (!ngram && !g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
   dj.draft_tokens = (const long long*)draft_tokens; dj.u_accept = u_accept; dj.u_sample = u_sample;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = gamma;
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = flags;
@@ -2071,7 +2137,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2087,6 +2153,9 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "mega_keep_l2")) { g_mega_keep_l2 = value; return 0; }
   if (!strcmp(name, "mega_dbg")) { g_mega_dbg = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
+  if (!strcmp(name, "no_klist")) { g_no_klist = value; return 0; }
+  if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
+  if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }
   if (!strcmp(name, "no_hist_nucleus")) { g_no_hist_nucleus = value; return 0; }
   if (!strcmp(name, "no_tma_nucleus")) { g_no_tma_nucleus = value; return 0; }
   if (!strcmp(name, "no_fast_ngram")) { g_no_fast_ngram = value; return 0; }
@@ -2159,6 +2228,7 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
                        workspace_bytes);
   if (rc) return rc;
   int* scratch = (int*)((char*)workspace + wl.total);
+  if (!g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
   dj.draft_tokens = nullptr; dj.u_accept = nullptr; dj.u_sample = u;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = 0;
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = 0; dj.stop = nullptr; dj.n_stop = 0;

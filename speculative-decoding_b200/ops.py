@@ -232,24 +232,36 @@ def philox_uniform_op(seed: int, offset: int, seq_id0: int, B: int, gamma: int, 
 
 
 @torch.library.custom_op("specdec::prune_kv", mutates_args={"tensors", "seq_lens"})
-def prune_kv_op(tensors: List[Tensor], seq_lens: Tensor, discard: Tensor, zero_fill: bool) -> None:
-    """Per-sequence KV rollback on static [B,H,S_max,D] cache tensors (utils/caching.py:27-55 generalised)."""
+def prune_kv_op(tensors: List[Tensor], seq_lens: Tensor, discard: Tensor, zero_fill: bool, ptrs: Optional[Tensor]) -> None:
+    """Per-sequence KV rollback on static [B,H,S_max,D] cache tensors (utils/caching.py:27-55 generalised).
+    ptrs: optional cached device table of the tensors' addresses (int64 [n]); without zero_fill only the
+    length vector changes and the tensors are not touched at all."""
     _need_cuda(seq_lens, discard, *tensors)
     if not tensors:
         return
     B, H, S, D = tensors[0].shape
-    for t in tensors:
-        if t.shape != (B, H, S, D) or not t.is_contiguous() or t.dtype != tensors[0].dtype:
-            raise ValueError("prune_kv: all cache tensors must be contiguous [B,H,S_max,D] of one dtype")
     if seq_lens.dtype != torch.int32 or not seq_lens.is_contiguous():
         raise ValueError("prune_kv: seq_lens must be a contiguous int32 tensor (updated in place)")
     dev = seq_lens.device
-    discard = discard.to(device=dev, dtype=torch.int32).contiguous()
-    ptrs = torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=dev)
+    if discard.dtype != torch.int32 or discard.device != dev or not discard.is_contiguous():
+        discard = discard.to(device=dev, dtype=torch.int32).contiguous()
+    n = 0
+    if zero_fill:
+        for t in tensors:
+            if t.shape != (B, H, S, D) or not t.is_contiguous() or t.dtype != tensors[0].dtype:
+                raise ValueError("prune_kv: all cache tensors must be contiguous [B,H,S_max,D] of one dtype")
+        if ptrs is None:
+            ptrs = kv_pointer_table(tensors)
+        n = len(tensors)
     with torch.cuda.device(dev):
-        rc = L.lib().specdec_prune_kv(_ptr(ptrs), len(tensors), B, H, S, D, tensors[0].element_size(),
+        rc = L.lib().specdec_prune_kv(_ptr(ptrs) if n else None, n, B, H, S, D, tensors[0].element_size(),
                                       _ptr(seq_lens), _ptr(discard), 1 if zero_fill else 0, _stream())
     L.check(rc, "specdec_prune_kv")
+
+
+def kv_pointer_table(tensors) -> Tensor:
+    """Device array of the cache tensors' addresses (build once per cache: StaticKVCache caches it)."""
+    return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=tensors[0].device)
 
 
 # ---- convenient python wrappers -------------------------------------------------------------
@@ -292,6 +304,8 @@ def philox_uniform(seed, offset, seq_id0, B, gamma, device="cuda"):
     return philox_uniform_op(int(seed), int(offset), int(seq_id0), int(B), int(gamma), torch.device(device))
 
 
-def prune_kv(tensors, seq_lens, discard, zero_fill=True):
-    prune_kv_op(list(tensors), seq_lens, discard, bool(zero_fill))
+def prune_kv(tensors, seq_lens, discard, zero_fill=False, ptrs=None):
+    """zero_fill=False (default): only the length vector is updated -- the valid prefix [0, len_b) is the
+    reference's pruned view; zero_fill=True also clears the discarded positions."""
+    prune_kv_op(list(tensors), seq_lens, discard, bool(zero_fill), ptrs)
     return seq_lens

@@ -94,6 +94,7 @@ def test_prune_kv_matches_reference_view_semantics(oracle_mod):
     gen = torch.Generator().manual_seed(0)
     tensors = [torch.randn(B, H, S, D, generator=gen).to(torch.bfloat16) for _ in range(4)]
     lens = torch.tensor([40, 17, 5, 1, 0], dtype=torch.int32)
+    lens0 = lens.clone()  # (the oracle updates the array it is given in place)
     disc = torch.tensor([3, 5, 5, 4, 2], dtype=torch.int32)
     dev = [t.cuda() for t in tensors]
     dl = lens.cuda()
@@ -105,10 +106,25 @@ def test_prune_kv_matches_reference_view_semantics(oracle_mod):
         assert np.array_equal(a.cpu().view(torch.int16).numpy(), b)
     # the valid prefix equals the reference's per-sequence view tensor[:, :, :-n, :]
     for b in range(B):
-        n = int(min(disc[b], lens[b])); L0 = int(lens[b])
+        n = int(min(disc[b], lens0[b])); L0 = int(lens0[b])
         if L0 - n > 0:
             ref_view = tensors[0][b:b + 1, :, :L0, :][:, :, :L0 - n, :] if n > 0 else tensors[0][b:b + 1, :, :L0, :]
             assert torch.equal(dev[0][b:b + 1, :, :L0 - n, :].cpu(), ref_view)
+    # default rollback = the length vector only (one tiny launch): the tensors are not touched, the valid prefix
+    # [0, len_b) is the reference's pruned view; StaticKVCache caches its device pointer table for zero fills
+    dev2 = [t.cuda() for t in tensors]
+    kv = sd.StaticKVCache(dev2, lens0.cuda())
+    kv.rollback(disc.cuda())
+    assert np.array_equal(kv.seq_lens.cpu().numpy(), new)
+    for a, b in zip(dev2, tensors):
+        assert torch.equal(a.cpu(), b)
+    kv2 = sd.StaticKVCache([t.cuda() for t in tensors], lens0.cuda())
+    kv2.rollback(disc.cuda(), zero_fill=True)
+    kv2.rollback(0, zero_fill=True)
+    for a, b in zip(kv2.tensors, exp):
+        assert np.array_equal(a.cpu().view(torch.int16).numpy(), b)
+    tv = kv2.as_tuple_views(1)
+    assert tv[0][0].shape == (1, H, 12, D)
     # drop-in prune_cache on tuple caches is the same zero-copy view as the reference
     cache = tuple((t[:1], t[:1]) for t in dev[:2])
     pr = sd.prune_cache(cache, 4)

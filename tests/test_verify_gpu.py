@@ -665,3 +665,87 @@ def test_megakernel_matches_oracle_and_three_launch_pipeline(oracle_mod, B, gamm
         for a, b_ in ((r0.n_accepted, r1.n_accepted), (r0.next_token, r1.next_token), (r0.accept_mask, r1.accept_mask),
                       (r0.packed, r1.packed), (r0.next_prob, r1.next_prob), (r0.first_stop, r1.first_stop)):
             assert torch.equal(a, b_)
+
+
+@pytest.mark.parametrize("mode", ["topk50", "topk50_p0.9", "nucleus0.9", "greedy_topk"])
+@pytest.mark.parametrize("flags,sigma", [(0, 0.5), (F_SKIP, 0.5), (F_BATCHED | F_NO_BONUS | F_FALLBACK, 0.0), (0, 0.0), (F_NO_BONUS, 2.0)])
+def test_kept_list_sampling_equals_row_sweep(oracle_mod, mode, flags, sigma):
+    """masked modes with small kept sets (top-k, top-k + top-p, LLM-like top-p): the next token is drawn from the
+    kept-token lists the selection kernels emit (sample_lists_kernel) -- bit-identical to the sweep over the row
+    ("no_klist"=1) and to the oracle, incl. greedy, the zero-residual fallback (p == q) and all flag variants."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g, V = 37, 4, 128256
+    m = dict(MODES["topk50"], greedy=True) if mode == "greedy_topk" else MODES[mode]
+    case = make_case(B=B, gamma=g, V=V, dtype="bf16", sigma=sigma, seed=66, kind="peaked")
+    gq = torch.Generator().manual_seed(6)
+    t = case["target"].float() * 0.5
+    idx = torch.randint(V, (B, g + 1, 24), generator=gq)
+    t.scatter_(2, idx, 12.0 + 8.0 * torch.rand(B, g + 1, 24, generator=gq))
+    t[0, :, 100:130] = 19.0   # a 30-way tie at the top: the top-k boundary falls inside a tie group
+    t[1, :, 5000:5080] = 21.0  # an 80-way tie: more kept tokens than a list holds -> that sequence takes the sweep
+    d = t[:, :g] + sigma * torch.randn(B, g, V, generator=gq)
+    case["target"], case["draft"] = t.to(torch.bfloat16), d.to(torch.bfloat16)
+    tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(B * g, V),
+                                    torch.rand(B * g, generator=torch.Generator().manual_seed(4)).numpy(), **m)
+    case["draft_tokens"] = torch.from_numpy(tok.reshape(B, g))
+    tgt = case["target"][:, :-1] if (flags & F_NO_BONUS) else case["target"]
+    args = [tgt.cuda(), case["draft"].cuda(), case["draft_tokens"].cuda(), case["u_accept"].cuda(), case["u_sample"].cuda()]
+    r1 = sd.fused_verify(*args, flags=flags, **m)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"no_klist", 1) == 0
+    r2 = sd.fused_verify(*args, flags=flags, **m)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"no_klist", 0) == 0
+    for a, b_ in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.p_tok, r2.p_tok), (r1.q_tok, r2.q_tok),
+                  (r1.accept_mask, r2.accept_mask), (r1.packed, r2.packed), (r1.next_prob, r2.next_prob)):
+        assert torch.equal(a, b_)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], flags=flags, **m)
+    _assert_same(o, r1)
+    # the drafter-side sampling op takes the same route
+    tk1, pt1 = sd.sample_rows(case["draft"].cuda().reshape(B * g, V), None, seed=5, **m)
+    assert lib.specdec_set_option(b"no_klist", 1) == 0
+    tk2, pt2 = sd.sample_rows(case["draft"].cuda().reshape(B * g, V), None, seed=5, **m)
+    assert lib.specdec_set_option(b"no_klist", 0) == 0
+    assert torch.equal(tk1, tk2) and torch.equal(pt1, pt2)
+
+
+@pytest.mark.parametrize("mode", ["topk50", "topk50_p0.9", "nucleus0.9", "nucleus0.9_t0.7"])
+@pytest.mark.parametrize("kind,dtype,V", [("peaked", "bf16", 128256), ("randn", "bf16", 128256), ("peaked", "f16", 50264),
+                                          ("randn", "bf16", 1000)])
+def test_streamed_selection_kernel_equals_exact_kernels(oracle_mod, mode, kind, dtype, V):
+    """masked modes on 16-bit rows: rowsel_tma_kernel (TMA-streamed pass, threshold among the slice maxima, gather of
+    the hot slices from L2, exact selection by a selector warp) gives bit-identical kept sets / probabilities /
+    decisions to the plain-load kernels ("no_rowsel"=1) and equals the oracle; rows it cannot resolve (flat top-p rows,
+    candidate overflow) fall through to those kernels."""
+    import specdec_b200 as sd
+    lib = sd._lib.lib()
+    B, g = 10, 3
+    case = make_case(B=B, gamma=g, V=V, dtype=dtype, sigma=0.4, seed=55, kind=kind)
+    if kind == "peaked":  # LLM-like: a handful of tokens carry almost all the mass
+        gq = torch.Generator().manual_seed(6)
+        t = case["target"].float() * 0.5
+        idx = torch.randint(V, (B, g + 1, 24), generator=gq)
+        t.scatter_(2, idx, 12.0 + 8.0 * torch.rand(B, g + 1, 24, generator=gq))
+        t[0, :, 100:140] = 19.0     # a 40-way tie at the top (the top-k boundary inside a tie group)
+        t[1, :, 0:3000] = 18.0      # a 3000-way tie: more candidates than the buffer holds -> falls through
+        t[2, :, 8 * 7::8 * 256] = 17.0  # every candidate in ONE thread's slice
+        d = t[:, :g] + 0.4 * torch.randn(B, g, V, generator=gq)
+        case["target"], case["draft"] = t.to(case["target"].dtype), d.to(case["target"].dtype)
+    m = MODES[mode]
+    tok, _ = oracle_mod.sample_rows(case["draft"].float().numpy().reshape(B * g, V),
+                                    torch.rand(B * g, generator=torch.Generator().manual_seed(4)).numpy(), **m)
+    case["draft_tokens"] = torch.from_numpy(tok.reshape(B, g))
+    args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    r1 = sd.fused_verify(*args, **m)
+    p1, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    assert lib.specdec_set_option(b"no_rowsel", 1) == 0
+    r2 = sd.fused_verify(*args, **m)
+    p2, _ = sd.process_probs(case["target"].cuda(), m["temperature"], m["top_k"], m["top_p"])
+    assert lib.specdec_set_option(b"no_rowsel", 0) == 0
+    assert torch.equal(p1, p2), "kept set / probabilities differ from the plain-load kernels"
+    for a, b_ in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.p_tok, r2.p_tok), (r1.q_tok, r2.q_tok),
+                  (r1.accept_mask, r2.accept_mask)):
+        assert torch.equal(a, b_)
+    o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], **m)
+    _assert_same(o, r1)
