@@ -118,6 +118,63 @@ def make_inputs(torch, B, gamma, V, dtype, sigma, seed, device, nbuf):
     return sets
 
 
+def config_dict(args, world):
+    """Same dict for both arms (the driver compares them)."""
+    B, g, V, dtype = args.B, args.gamma, args.V, args.dtype
+    per = "B=%d/gpu" % B if args.scaling == "weak" else "B=%d global (%d/gpu)" % (B, B // world)
+    ab = alg_bytes(B if args.scaling == "weak" else B // world, g, V, dtype)
+    return {"workload": f"synthetic logits verify: {per} gamma={g} V={V} {dtype} mode={args.mode} "
+                        f"sigma={args.sigma} (BASELINE.json configs[1])",
+            "l2": f"inputs {ab / 1e6:.0f} MB per step and GPU > 126 MB L2, rotated over {args.nbuf} buffers"
+                  if ab > 126e6 * 1.5 else
+                  f"inputs {ab / 1e6:.0f} MB per step and GPU, rotated over {args.nbuf} buffers (sum > 126 MB L2)",
+            "parallelism": f"dp{world} (sequences sharded by rank, all-gather of packed results)"}
+
+
+def count_our_launches(torch, step_fn, n=2):
+    """Kernels of the library (namespace specdec::) observed by CUPTI (torch.profiler) over n steps -> (per step, by name)."""
+    from torch.profiler import profile, ProfilerActivity
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        for i in range(n):
+            step_fn(i)
+        torch.cuda.synchronize()
+    by = {}
+    for ev in prof.key_averages():
+        if "specdec::" in ev.key:
+            short = ev.key.split("specdec::")[1].split("<")[0].split("(")[0]
+            by[short] = by.get(short, 0) + ev.count
+    tot = sum(by.values())
+    if tot == 0:
+        raise RuntimeError("profiler saw no specdec:: kernels")
+    return tot / n, {k: v / n for k, v in by.items()}
+
+
+def numa_local(local_gpu):
+    """Pin this process to the CPUs of the GPU's NUMA node before the pinned host buffers are allocated (first touch):
+    with 8 ranks copying 591 MB per step each, buffers on one node halve the H2D rate of the far GPUs."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_gpu).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_gpu).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_gpu).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cl = open(f"/sys/devices/system/node/node{node}/cpulist").read().strip()
+        cpus = set()
+        for part in cl.split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        return None
+    return None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -131,7 +188,13 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B, g, V, dtype = args.B, args.gamma, args.V, args.dtype
+    Bglob = args.B
+    if args.scaling == "strong":
+        assert args.B % world == 0, "strong scaling shards the global batch evenly"
+        args_B_local = args.B // world
+    else:
+        args_B_local = args.B
+    B, g, V, dtype = args_B_local, args.gamma, args.V, args.dtype
     mode = MODES[args.mode]
     nbuf = args.nbuf
     sets = make_inputs(torch, B, g, V, dtype, args.sigma, rank, dev, nbuf)
@@ -260,8 +323,75 @@ def run_ours(args):
         except Exception as ex:  # reported as absent, never fatal for the bench line
             print(f"[bench] graph replay skipped: {ex}", file=sys.stderr)
 
+    # ---- kernels of ours per step, OBSERVED (CUPTI through torch.profiler, two untimed steps)
+    launches_src = "observed: CUPTI kernel records named specdec::* over 2 untimed steps x K"
+    try:
+        per_step, by_name = count_our_launches(torch, step)
+        drain()
+    except Exception as ex:
+        per_step, by_name = 3 * (2 if pipelined else 1), {}
+        launches_src = f"computed (profiler unavailable: {str(ex)[:80]})"
+    sync_all()
+
+    # ---- two independent batches in flight on two streams (a serving engine that pipelines micro-batches): the exact
+    # tail of one batch overlaps the HBM-bound row pass of the other.  Reported, NOT the headline: per-step latency
+    # is unchanged, only the throughput of back-to-back independent steps rises.
+    ms_two = None
+    if world == 1:
+        try:
+            s2 = [torch.cuda.Stream(), torch.cuda.Stream()]
+            for s_ in s2:
+                s_.wait_stream(torch.cuda.current_stream())
+            def two(n):
+                for i in range(n):
+                    with torch.cuda.stream(s2[i & 1]):
+                        sd.fused_verify(sets[i % nbuf][0], sets[i % nbuf][1], toks[i % nbuf], None, None, seed=2025,
+                                        offset=i, seq_id0=seq0, **mode)
+            two(4)
+            torch.cuda.synchronize()
+            e0.record()
+            for s_ in s2:
+                s_.wait_event(e0)
+            two(K)
+            for s_ in s2:
+                torch.cuda.current_stream().wait_stream(s_)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_two = e0.elapsed_time(e1) / K
+        except Exception as ex:
+            print(f"[bench] two-batch pipelining skipped: {ex}", file=sys.stderr)
+
+    # ---- strong scaling (BASELINE.json configs[4]: the GLOBAL batch sharded across the GPUs) next to the weak line
+    strong = None
+    if world > 1 and args.scaling == "weak" and Bglob % world == 0:
+        Bs_ = Bglob // world
+        def sstep(i):
+            t, d = sets[i % nbuf]
+            r = sd.fused_verify(t[:Bs_], d[:Bs_], toks[i % nbuf][:Bs_], None, None, seed=2025, offset=i,
+                                seq_id0=rank * Bs_, **mode)
+            out_, work = sd.dist.all_gather_packed(r.packed, world * Bs_, async_op=True)
+            pending.append(work)
+            if len(pending) > 2:
+                pending.pop(0).wait()
+        for i in range(5):
+            sstep(i)
+        drain()
+        sync_all()
+        e0.record()
+        for i in range(K):
+            sstep(i)
+        drain()
+        e1.record()
+        sync_all()
+        tt = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_s = float(tt[0]) / K
+        strong = {"global_B": Bglob, "B_per_gpu": Bs_, "ms_per_step": ms_s, "value": Bglob * g / (ms_s * 1e-3),
+                  "unit": "tokens/s", "note": "same timing rules; value(N) / value at N=1 of the weak line = strong-scaling speed-up"}
+
     # ---- e2e: HOST logits (pinned) -> H2D -> verify -> D2H packed result, all inside the timed region
     t0, d0 = sets[0]
+    numa = numa_local(local) if world > 1 else None
     ht = torch.empty(t0.shape, dtype=t0.dtype, pin_memory=True).copy_(t0)
     hd = torch.empty(d0.shape, dtype=d0.dtype, pin_memory=True).copy_(d0)
     htok = torch.empty(toks[0].shape, dtype=toks[0].dtype, pin_memory=True).copy_(toks[0])
@@ -373,6 +503,37 @@ def run_ours(args):
             sweep[f"{args.mode}_B{Bs}"] = {"tokens_per_s": Bs * g / (msm * 1e-3), "ms_per_step": msm,
                                            "step_frac_of_hbm_peak": alg_bytes(Bs, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
 
+        # ---- the rest of BASELINE.json configs[1] (dtype / vocabulary / gamma axes) and the configs[2] shape
+        # (B=64, gamma=4, nucleus p=0.9), each on its own inputs (two rotated sets; sets below the L2 size say so)
+        def sweep_case(name, Bc, gc, Vc, dtc, mname, steps_=20):
+            md = MODES[mname]
+            ss = make_inputs(torch, Bc, gc, Vc, dtc, args.sigma, 7, dev, 2)
+            tk = [sd.sample_rows(d_.reshape(Bc * gc, Vc), None, seed=4321, offset=0, seq_id0=0, **md)[0].reshape(Bc, gc)
+                  for (_, d_) in ss]
+            for i in range(3):
+                sd.fused_verify(ss[i % 2][0], ss[i % 2][1], tk[i % 2], None, None, seed=1, offset=i, **md)
+            torch.cuda.synchronize()
+            e0.record()
+            for i in range(steps_):
+                sd.fused_verify(ss[i % 2][0], ss[i % 2][1], tk[i % 2], None, None, seed=1, offset=i, **md)
+            e1.record()
+            torch.cuda.synchronize()
+            msm = e0.elapsed_time(e1) / steps_
+            abc = alg_bytes(Bc, gc, Vc, dtc)
+            sweep[name] = {"tokens_per_s": Bc * gc / (msm * 1e-3), "ms_per_step": msm,
+                           "step_frac_of_hbm_peak": abc / (msm * 1e-3) / 1e9 / peaks()[0],
+                           "inputs_mb": abc / 1e6, "l2": "2 rotated sets" + ("" if 2 * abc > 126e6 else " (fit the 126 MB L2)")}
+            del ss
+        try:
+            sweep_case("configs2_B64_g4_V128256_bf16_nucleus0.9", 64, 4, 128256, "bf16", "nucleus0.9", 10)
+            sweep_case("B256_g4_V128256_f32_multinomial", 256, 4, 128256, "f32", "multinomial")
+            sweep_case("B256_g4_V32000_bf16_multinomial", 256, 4, 32000, "bf16", "multinomial")
+            sweep_case("B256_g1_V128256_bf16_multinomial", 256, 1, 128256, "bf16", "multinomial")
+            sweep_case("B256_g8_V128256_bf16_multinomial", 256, 8, 128256, "bf16", "multinomial")
+            sweep_case("B256_g4_V32000_f32_topk50", 256, 4, 32000, "f32", "topk50")
+        except Exception as ex:
+            sweep["sweep_case_error"] = str(ex)[:200]
+
         # ---- the two companion kernels of the path, reported as secondary numbers
         try:
             # KV rollback: Llama-3-8B-like static cache slice, 8 layers x (K,V), B=64, H_kv=8, S=2048, D=128, bf16
@@ -445,13 +606,12 @@ def run_ours(args):
         out = {
             "metric": "verified draft tokens/s (B=256, gamma=4, V=128k)", "value": value, "unit": "tokens/s",
             "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": dtype, "data": "synthetic",
-            "config": {"workload": f"synthetic logits verify: B={B}/gpu gamma={g} V={V} {dtype} mode={args.mode} "
-                                   f"sigma={args.sigma} (BASELINE.json configs[1])",
-                       "l2": f"inputs {ab / 1e6:.0f} MB per step > 126 MB L2, rotated over {nbuf} buffers",
-                       "parallelism": f"dp{world} (sequences sharded by rank, all-gather of packed results)"},
+            "scaling": args.scaling, "vs_baseline": None, "dtype": dtype, "data": "synthetic",
+            "config": config_dict(args, world),
             "roofline": {"bound": "hbm", "kernel": "rowfast_tma_kernel" if dtype != "f32" else "rowfast_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": ach / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": ach / peak, "traffic": traffic,
+                         "traffic_source": "ncu --set full capture of one full-batch launch (profiles/r1_traffic.json), dram read+write bytes",
+                         "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "kernel_ms": t_rowstats, "decide_kernel_ms": t_decide,
                          "kernel_timed": ("alone: separate pass with the two-chunk stream pipelining off, one launch "
                                           "reads all algorithmic bytes" if pipelined else "inside the timed steps"),
@@ -459,12 +619,15 @@ def run_ours(args):
                          "split_timed": "instrumented passes outside the K timed steps (event hooks cost ~10 us per step)",
                          "step_frac": ab / (ms_step * 1e-3) / 1e9 / peak},
             "e2e": {"value": e2e_val, "unit": "tokens/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / Ke},
-            # kernels of ours inside the timed region: per verify call (row kernel, plan, fused tail) x chunks
-            "gpu_launches": K * 3 * (2 if pipelined else 1),
+                    "ms_per_step": ms_e2e / Ke, "pinned_buffers_numa_node": numa},
+            # kernels of ours inside the timed region
+            "gpu_launches": int(round(K * per_step)), "gpu_launches_per_step": by_name, "gpu_launches_source": launches_src,
             "graph_replay_ms_per_step": ms_graph,
+            "two_batches_in_flight_ms_per_step": ms_two,
             "clocks": clocks,
         }
+        if strong is not None:
+            out["strong_scaling"] = strong
         if sweep:
             out["sweep"] = sweep
     if world > 1:
@@ -474,12 +637,13 @@ def run_ours(args):
 
 
 def cpu_reference_leg(args, steps, warmup, all_threads=True):
-    """The reference's CPU path for the same workload, on a bounded sample (B_s sequences of the same
-    shape), timed on this host's cores.  kind = "port": oracle/torch_port.py restates the reference's
-    torch-eager arithmetic (utils/logits_processor.py + sampling/speculative_decoding.py:135-171);
-    /root/reference itself is not available on the GPU box."""
+    """The reference's CPU path for the same workload, on a bounded sample (B_s sequences of the same shape), timed on
+    this host's cores.  kind = "reference": oracle/_ref holds the UNMODIFIED reference files (oracle/make_ref.py) and
+    oracle/ref_arm.py drives one speculative step per sequence through the reference's own speculative_generate
+    (sampling/speculative_decoding.py:107-172) and LogitsProcessor classes; kind = "port" (only when oracle/_ref did not
+    travel): oracle/torch_port.py, the torch-eager restatement checked bit for bit against the reference."""
     import torch
-    from oracle import torch_port
+    from oracle import ref_arm, torch_port
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores if all_threads else 1)
     Bs = args.cpu_sample_B
@@ -490,17 +654,29 @@ def cpu_reference_leg(args, steps, warmup, all_threads=True):
     d = (t[:, :g] + args.sigma * torch.randn(Bs, g, V, generator=gen)).to(dt)
     t = t.to(dt)
     mode = MODES[args.mode]
-    toks = torch.stack([torch_port.sample_rows(d[b], mode, gen) for b in range(Bs)])
+    kind = "reference" if ref_arm.available() else "port"
+    if kind == "reference":
+        # the reference's models emit fp32 logits on CPU: same VALUES as the GPU arm's rows, upcast outside the timing
+        tf, df = t.float(), d.float()
+        proc = ref_arm.make_processor(mode)
+        one = lambda b: ref_arm.verify_step(tf[b], df[b], mode, proc)
+    else:
+        toks = torch.stack([torch_port.sample_rows(d[b], mode, gen) for b in range(Bs)])
+        one = lambda b: torch_port.verify_one(t[b], d[b], toks[b], mode, gen)
     times = []
     for i in range(warmup + steps):
         t0 = time.perf_counter()
         for b in range(Bs):  # the reference is batch-1: one sequence per call
-            torch_port.verify_one(t[b], d[b], toks[b], mode, gen)
+            one(b)
         times.append(time.perf_counter() - t0)
     times = times[warmup:]
     ms = 1e3 * sum(times) / len(times)
     val = Bs * g / (ms * 1e-3)
-    return val, ms, cores, f"{Bs} of {args.B} sequences per step (same shape), {len(times)} timed steps, torch {torch.__version__} CPU, {torch.get_num_threads()} threads"
+    what = ("unmodified reference (oracle/_ref: speculative_generate + LogitsProcessor, fp32 logits)" if kind == "reference"
+            else "torch-eager port of the reference arithmetic (oracle/torch_port.py)")
+    return {"value": val, "ms_sample": ms, "ms_full_batch": ms * args.B / Bs, "cores": cores, "kind": kind, "timed_steps": len(times),
+            "sample": f"{Bs} of {args.B} sequences per step (same shape and values), {len(times)} timed steps, {what}, "
+                      f"torch {torch.__version__} CPU, {torch.get_num_threads()} threads"}
 
 
 def main():
@@ -520,6 +696,8 @@ def main():
     ap.add_argument("--cpu-sample-B", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: B sequences per GPU (default); strong: B is the global batch, sharded across the GPUs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", 0))
@@ -527,23 +705,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        val, ms, cores, sample = cpu_reference_leg(args, max(1, min(args.steps, 3)), min(args.warmup, 1))
+        # each "step" = the bounded sample (cpu_sample_B sequences); as many steps as asked for, capped so that the
+        # whole run stays within a few minutes; `steps` reports what was actually timed, `ms_per_step` is scaled to
+        # the full batch of B sequences (the sample is B_s / B of a step)
+        r = cpu_reference_leg(args, max(1, min(args.steps, 20)), max(1, min(args.warmup, 2)))
         print(json.dumps({
-            "impl": "reference", "metric": "verified draft tokens/s (B=256, gamma=4, V=128k)", "value": val,
-            "unit": "tokens/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-            "config": {"workload": f"synthetic logits verify: B={args.B}/gpu gamma={args.gamma} V={args.V} {args.dtype} "
-                                   f"mode={args.mode} sigma={args.sigma} (BASELINE.json configs[1])"},
-            "cpu_baseline": {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample},
-            "e2e": {"value": val, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "impl": "reference", "metric": "verified draft tokens/s (B=256, gamma=4, V=128k)", "value": r["value"],
+            "unit": "tokens/s", "n_gpus": args.gpus, "steps": r["timed_steps"], "steps_requested": args.steps,
+            "warmup": max(1, min(args.warmup, 2)), "ms_per_step": r["ms_full_batch"], "ms_per_sample_step": r["ms_sample"],
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": config_dict(args, args.gpus),
+            "cpu_baseline": {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
 
     out = run_ours(args)
     if rank == 0 and out is not None:
         if args.gpus == 1 and not args.no_cpu_baseline:
             try:
-                val, ms, cores, sample = cpu_reference_leg(args, 2, 1)
-                out["cpu_baseline"] = {"value": val, "unit": "tokens/s", "cores": cores, "kind": "port", "sample": sample}
+                r = cpu_reference_leg(args, 3, 1)
+                out["cpu_baseline"] = {"value": r["value"], "unit": "tokens/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
             except Exception as e:  # the baseline is a reported number; never lose the GPU line over it
                 out["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": os.cpu_count(), "kind": "port",
                                        "sample": f"failed: {e}"}

@@ -45,6 +45,12 @@ typedef struct CUstream_st* specdec_stream_t; /* == cudaStream_t */
 #define SPECDEC_SKIP_ADJUST 4     /* skip_sample_adjustment (sampling/speculative_decoding.py:167-170) */
 #define SPECDEC_NGRAM 8           /* accept iff draft==sample(p_i); no drafter logits (ngram_assisted/ngram_assisted.py:114-141) */
 #define SPECDEC_RESID_FALLBACK 16 /* residual mass <= 1e-12 -> sample from p (engine/infer_engine.py:319-321) */
+#define SPECDEC_OFFSET_DEVICE 32  /* philox_offset is the ADDRESS of a uint64 in device memory; the kernels read the word
+                                     when they run, so a captured CUDA graph / device-resident decode loop
+                                     (engine/infer_engine.py:211-338 without host scalars) advances its uniforms by
+                                     bumping that word.  specdec_sample_rows: same meaning, signalled by
+                                     lane_id | SPECDEC_LANE_OFFSET_DEVICE */
+#define SPECDEC_LANE_OFFSET_DEVICE (1 << 30)
 
 #define SPECDEC_ERR_ARG (-1)
 #define SPECDEC_ERR_WORKSPACE (-2)
@@ -183,6 +189,29 @@ SPECDEC_API int specdec_ngram_lookup_chain(specdec_ngram_t* t, const int64_t* id
                                uint8_t* known, specdec_stream_t stream);
 /* device int32[2]: {overflow flag, entries used (max over tables)} */
 SPECDEC_API int specdec_ngram_status(specdec_ngram_t* t, int32_t* host_out2);
+
+/*
+ * Decode-loop helpers (csrc/engine.cu).
+ *
+ * specdec_topk_ids: ids of the k largest logits of each row, value descending / index ascending on ties, -1 when the
+ * row has fewer than k elements -- the filler tokens of ngram_assisted/ngram_assisted.py:149-155
+ * (`torch.topk(p[..., i, :], filler_top_k)`; probabilities are monotone in the logits, no V-wide probability row is
+ * written).  out_ids [rows, k] int64.
+ *
+ * specdec_batch_writeback: the per-sequence bookkeeping after a batched verify (engine/infer_engine.py:300-336) on
+ * device-resident state, one launch, no host read-back: for every sequence with finished[b] == 0
+ *   acc = first_stop >= 0 ? first_stop + 1 : n_accepted;  n_acc[b] += acc;
+ *   rejected (no stop, n < gamma): generated[b, step + n] = next_token;  generated[b, step + acc + 1 ..] = 0;
+ *   finished[b] = stop hit || (rejected && next_token is an end token).
+ * step: host value, or read from *step_dev when step_dev != NULL (graph-captured loops).  n_active_out (nullable):
+ * device int32 that receives the number of sequences still running.
+ */
+SPECDEC_API int specdec_topk_ids(const void* logits, int dtype, int64_t rows, int V, int64_t row_stride, int k, int64_t* out_ids,
+                     specdec_stream_t stream);
+SPECDEC_API int specdec_batch_writeback(int B, int gamma, const int32_t* n_accepted, const int32_t* first_stop,
+                            const int64_t* next_token, int64_t* generated, int64_t gen_stride, const int64_t* step_dev,
+                            int64_t step, uint8_t* finished, int64_t* n_acc, const int64_t* end_tokens, int n_end,
+                            int32_t* n_active_out, specdec_stream_t stream);
 
 #ifdef __cplusplus
 }

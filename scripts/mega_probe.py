@@ -33,7 +33,7 @@ def run(B, n=20, **opts):
 for B in [int(x) for x in os.environ.get("BS", "1,8,32,64,128,256").split(",")]:
     if B > Bmax: continue
     ms0, r0 = run(B, n=int(os.environ.get("N", 20)), mega=0)
-    ms1, r1 = run(B, n=int(os.environ.get("N", 20)))
+    ms1, r1 = run(B, n=int(os.environ.get("N", 20)), mega=1)
     same = all(torch.equal(a, b) for a, b in ((r0.n_accepted, r1.n_accepted), (r0.next_token, r1.next_token),
                                               (r0.accept_mask, r1.accept_mask), (r0.packed, r1.packed)))
     print(f"B={B:4d}  three-launch {ms0*1e3:8.1f} us   mega {ms1*1e3:10.1f} us   same={same}", flush=True)
@@ -41,7 +41,7 @@ def timeline(B):
     import numpy as np
     from specdec_b200 import ops
     lib.specdec_set_option(b"reset", 1)
-    lib.specdec_set_option(b"mega_dbg", 1)
+    lib.specdec_set_option(b"mega_dbg", 1); lib.specdec_set_option(b"mega", 1)
     for i in range(3):
         sd.fused_verify(t[:B], d[:B], toks[:B], None, None, seed=7, offset=i)
     torch.cuda.synchronize()
@@ -85,6 +85,6 @@ if os.environ.get("SWEEP"):
     B = Bmax
     for opts in [dict(mega_r=1), dict(mega_r=3), dict(mega_unit=2), dict(mega_unit=8), dict(mega_unit=16), dict(mega_keep_l2=0),
                  dict(mega_spc=12), dict(mega_spc=16), dict(mega_spc=20)]:
-        ms1, r1 = run(B, **opts)
+        ms1, r1 = run(B, mega=1, **opts)
         print(f"B={B} {opts}: mega {ms1*1e3:8.1f} us", flush=True)
 lib.specdec_set_option(b"reset", 1)

@@ -11,7 +11,8 @@ LIB_PATH = os.environ.get("SPECDEC_B200_LIB") or os.path.join(_HERE, "libspecdec
 
 F32, BF16, F16 = 0, 1, 2
 SAMPLE_GREEDY, SAMPLE_INVCDF = 0, 1
-ACCEPT_BATCHED, NO_BONUS, SKIP_ADJUST, NGRAM, RESID_FALLBACK = 1, 2, 4, 8, 16
+ACCEPT_BATCHED, NO_BONUS, SKIP_ADJUST, NGRAM, RESID_FALLBACK, OFFSET_DEVICE = 1, 2, 4, 8, 16, 32
+LANE_OFFSET_DEVICE = 1 << 30
 
 _vp, _i, _i64, _u64, _f, _sz = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_float, C.c_size_t
 
@@ -40,6 +41,8 @@ _SIGS = {
     "specdec_ngram_update": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _i, _vp]),
     "specdec_ngram_lookup_chain": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _i, _vp, _vp, _vp, _vp]),
     "specdec_ngram_status": (_i, [_vp, _vp]),
+    "specdec_topk_ids": (_i, [_vp, _i, _i64, _i, _i64, _i, _vp, _vp]),
+    "specdec_batch_writeback": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
 }
 
 _lib = None

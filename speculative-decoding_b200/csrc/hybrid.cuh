@@ -100,7 +100,7 @@ __device__ __forceinline__ void dbg_stamp_max(const HybridWs& ws, int slot) { if
 
 __device__ __forceinline__ float job_u_accept(const DecideJob& job, int b, int i) {
   return job.u_accept ? job.u_accept[(long long)b * job.gamma + i]
-                      : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)i);
+                      : philox_uniform(job.seed, job_offset(job), (unsigned)(job.seq0 + b), (unsigned)i);
 }
 __device__ __forceinline__ int accept_rule(float p, float q, float u, int flags) {
   if (flags & SPECDEC_ACCEPT_BATCHED) {  // engine/infer_engine.py:303-305 (python floats = double)
@@ -552,7 +552,7 @@ __device__ void finalize_sequence(const DecideJob& job, const HybridWs& ws, int 
   const int n = __ldcg(&ws.samp[b * SAMP_N + 0]), mode = __ldcg(&ws.samp[b * SAMP_N + 1]), prow = __ldcg(&ws.samp[b * SAMP_N + 2]);
   const bool greedy = job.greedy != 0;
   const float us = job.u_sample ? job.u_sample[b]
-                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
+                                : philox_uniform(job.seed, job_offset(job), (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
   u64* part = ws.part + (size_t)b * ws.nseg_pad;
   const long long r1 = (long long)b * rps + prow;
   const void* prow_ptr = row_ptr<DT>(rj, r1);
@@ -769,7 +769,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob j
   const float c = rj.c;
   const bool greedy = job.greedy != 0;
   const float us = job.u_sample ? job.u_sample[b]
-                                : philox_uniform(job.seed, job.offset, (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
+                                : philox_uniform(job.seed, job_offset(job), (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
   int* sj = s_j[wib]; float* sp = s_p[wib]; u64* sw = s_w[wib]; int* sqj = s_qj[wib]; float* sqz = s_qz[wib];
   // ---- load the lists; the target row's list sorted by token index (rank sort: KL_MAX^2 / 32 comparisons per lane)
   const int2* lp = rj.klist + r1 * KL_MAX;

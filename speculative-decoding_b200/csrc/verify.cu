@@ -1293,6 +1293,7 @@ struct DecideJob {
   const float* u_accept;
   const float* u_sample;
   u64 seed, offset;
+  const u64* offset_dev;  // SPECDEC_OFFSET_DEVICE: the offset lives in device memory and is read when the kernels RUN
   long long seq0;
   int gamma;
   int greedy;
@@ -1309,6 +1310,10 @@ struct DecideJob {
   int* packed;
   int lane_sample;  // philox lane of the sample stream
 };
+
+// Philox offset of the step: a host scalar, or (SPECDEC_OFFSET_DEVICE) a word in device memory, so that a replayed
+// CUDA graph / a device-resident decode loop advances its uniforms without new host arguments.
+__device__ __forceinline__ u64 job_offset(const DecideJob& job) { return job.offset_dev ? __ldg(job.offset_dev) : job.offset; }
 
 template <int DT>
 __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
@@ -1333,7 +1338,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
   // 1. per-position accept test
   if (ngram) {
     for (int i = 0; i < g; ++i) {  // accept iff draft == sample(p_i)  (ngram_assisted.py:114-119)
-      const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job.offset, seq, i);
+      const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job_offset(job), seq, i);
       const void* prow = row_ptr<DT>(rj, (long long)b * rps + i);
       const long long s = sample_p_row<DT>(prow, ro[i], V, c, greedy, u, sc);
       if (threadIdx.x == 0) {
@@ -1350,7 +1355,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
     const void* qrow = row_ptr<DT>(rj, (long long)b * rps + rj.nT + i);
     const float p = row_prob<DT>(ro[i], prow, tok, c);
     const float q = row_prob<DT>(ro[rj.nT + i], qrow, tok, c);
-    const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job.offset, seq, i);
+    const float u = job.u_accept ? job.u_accept[(long long)b * g + i] : philox_uniform(job.seed, job_offset(job), seq, i);
     int acc;
     if (job.flags & SPECDEC_ACCEPT_BATCHED) {  // engine/infer_engine.py:303-305 (python floats = double)
       const double ap = (q <= 0.0f) ? 1.0 : fmin(1.0, (double)p / (double)q);
@@ -1379,7 +1384,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
   const int n = s_n;
 
   // 2. next token
-  const float us = job.u_sample ? job.u_sample[b] : philox_uniform(job.seed, job.offset, seq, (unsigned)job.lane_sample);
+  const float us = job.u_sample ? job.u_sample[b] : philox_uniform(job.seed, job_offset(job), seq, (unsigned)job.lane_sample);
   long long x = -1;
   int prow_idx = -1;  // target row x was drawn from (for next_prob)
   if (n == g) {
@@ -2090,6 +2095,11 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
   if (!ngram && !g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
   dj.draft_tokens = (const long long*)draft_tokens; dj.u_accept = u_accept; dj.u_sample = u_sample;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = gamma;
+  dj.offset_dev = nullptr;
+  if (flags & SPECDEC_OFFSET_DEVICE) {
+    if (!philox_offset) return SPECDEC_ERR_ARG;
+    dj.offset_dev = (const u64*)(uintptr_t)philox_offset; dj.offset = 0;
+  }
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = flags;
   dj.stop = (const long long*)stop_tokens; dj.n_stop = n_stop;
   dj.n_acc = n_accepted; dj.next_tok = (long long*)next_token; dj.mask = accept_mask; dj.p_tok = p_tok;
@@ -2230,10 +2240,15 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
   int* scratch = (int*)((char*)workspace + wl.total);
   if (!g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
   dj.draft_tokens = nullptr; dj.u_accept = nullptr; dj.u_sample = u;
-  dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = 0;
+  dj.seed = philox_seed; dj.offset = philox_offset; dj.offset_dev = nullptr; dj.seq0 = seq_id0; dj.gamma = 0;
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = 0; dj.stop = nullptr; dj.n_stop = 0;
   dj.n_acc = scratch; dj.first_stop = scratch + rows; dj.next_tok = (long long*)tok; dj.mask = nullptr;
   dj.p_tok = nullptr; dj.q_tok = nullptr; dj.next_prob = ptok; dj.packed = nullptr;
+  if (lane_id & SPECDEC_LANE_OFFSET_DEVICE) {
+    if (!philox_offset) return SPECDEC_ERR_ARG;
+    lane_id &= ~SPECDEC_LANE_OFFSET_DEVICE;
+    dj.offset_dev = (const u64*)(uintptr_t)philox_offset; dj.offset = 0;
+  }
   dj.lane_sample = 0x20000 + lane_id;
   cudaStream_t st = (cudaStream_t)stream;
   DISPATCH_DT(dtype, {

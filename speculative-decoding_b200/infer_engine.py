@@ -8,7 +8,9 @@ What changes is the hot loop: the reference materialises q_probs_full/p_probs_fu
 (:221,:276) and then runs B*gamma Python iterations with >= 3 .item() syncs each (:280-336).  Here the
 drafter step is one specdec::sample_rows launch, the whole accept / residual-resample block is ONE
 specdec::verify launch (flags ACCEPT_BATCHED|NO_BONUS|RESID_FALLBACK) on the drafter's *logits*, and
-the write-back is vectorised torch indexing: no host sync inside a step.
+the write-back (accepted counts, corrected token, zeroed tail, finished flags) is ONE
+specdec_batch_writeback launch on device-resident state.  The Philox offset lives on the device and the
+"all finished" exit is polled from a pinned flag one step late, so no step waits for the host.
 """
 from __future__ import annotations
 
@@ -17,7 +19,7 @@ from typing import List, Tuple
 import torch
 
 from . import ops
-from .uniforms import PhiloxUniforms
+from .uniforms import PhiloxUniforms, default_uniforms  # noqa: F401
 
 _FLAGS = ops.L.ACCEPT_BATCHED | ops.L.NO_BONUS | ops.L.RESID_FALLBACK
 
@@ -26,7 +28,7 @@ _FLAGS = ops.L.ACCEPT_BATCHED | ops.L.NO_BONUS | ops.L.RESID_FALLBACK
 def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: torch.Tensor, batch_size: int,
                                first_token_callback=None, uniforms=None, seq_id0: int = 0
                                ) -> Tuple[List[torch.Tensor], List[float]]:
-    un = uniforms if uniforms is not None else PhiloxUniforms()
+    un = uniforms if uniforms is not None else default_uniforms()
     device = input_ids.device
     target_device = getattr(ctx, "target_device", device)
     B, G = batch_size, ctx.gen_len
@@ -39,9 +41,26 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
     out0 = ctx.drafter(input_ids, attention_mask=attention_mask, use_cache=True)
     drafter_past = out0.past_key_values
 
+    # ---- device-resident loop state: nothing below reads a device value on the host per step.
+    #  * Philox offset: one int64 word on the device, bumped by one tiny in-stream add per step; every kernel of the
+    #    step reads it when it RUNS (SPECDEC_OFFSET_DEVICE), lanes keep the calls of one step apart.
+    #  * finished / n_acc / generated are updated by ONE specdec_batch_writeback launch per step.
+    #  * the "all finished" early exit (:211) is polled one step late from a pinned flag (non-blocking copy + event):
+    #    an extra step on finished sequences changes nothing (they are masked out), so results are identical.
+    dev_off = None
+    if not un.injected:
+        dev_off = torch.full((1,), un.offset, dtype=torch.int64, device=device)
+    n_active = torch.zeros(1, dtype=torch.int32, device=device)
+    n_active_host = torch.ones(1, dtype=torch.int32).pin_memory() if device.type == "cuda" else None
+    poll_event = None
+    steps_run = 0
+
     step = 0
     while step < G:
-        if bool(finished.all()):
+        if un.injected:
+            if bool(finished.all()):
+                break
+        elif poll_event is not None and poll_event.query() and int(n_active_host[0]) == 0:
             break
         g = min(ctx.gamma, G - step)
         active = ~finished
@@ -62,7 +81,7 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
             if un.injected:
                 tok, _ = ops.sample_rows(logits, un.sample(B))
             else:
-                tok, _ = ops.sample_rows(logits, None, seed=un.seed, offset=un.next_offset(), seq_id0=seq_id0, lane_id=k)
+                tok, _ = ops.sample_rows(logits, None, seed=un.seed, offset=dev_off, seq_id0=seq_id0, lane_id=k)
             tok = tok.to(device)
             draft_tokens[:, k] = torch.where(active, tok, draft_tokens[:, k])
             generated[:, step + k] = torch.where(active, tok, generated[:, step + k])
@@ -79,26 +98,18 @@ def batch_speculative_generate(ctx, input_ids: torch.Tensor, attention_mask: tor
             res = _verify_injected(un, t_logits, draft_logits, draft_tokens, active, end_tokens)
         else:
             res = ops.fused_verify(t_logits, draft_logits, draft_tokens, None, None, seed=un.seed,
-                                   offset=un.next_offset(), seq_id0=seq_id0, flags=_FLAGS, stop_tokens=end_tokens)
-        n = res.n_accepted.long()
-        fs = res.first_stop.long()
-        x = res.next_token
-        # accepted drafts end at the first accepted end token (:310-312)
-        hit_end = fs >= 0
-        acc_cnt = torch.where(hit_end, fs + 1, n)
-        rejected = (~hit_end) & (n < g)
-        n_acc += torch.where(active, acc_cnt, torch.zeros_like(acc_cnt))
-        # corrected token at step+n, zeros after it (:326,:333-336)
-        ar = torch.arange(g, device=device)
-        cur = generated[:, step:step + g]
-        corr = rejected.unsqueeze(1) & (ar.unsqueeze(0) == n.unsqueeze(1))
-        cur = torch.where(corr, x.unsqueeze(1), cur)
-        tail = (acc_cnt < g).unsqueeze(1) & (ar.unsqueeze(0) >= (acc_cnt + 1).unsqueeze(1))
-        cur = torch.where(tail, torch.zeros_like(cur), cur)
-        generated[:, step:step + g] = torch.where(active.unsqueeze(1), cur, generated[:, step:step + g])
-        x_is_end = torch.isin(x, end_tokens) if end_tokens.numel() else torch.zeros_like(rejected)
-        finished = finished | (active & (hit_end | (rejected & x_is_end)))
+                                   offset=dev_off, seq_id0=seq_id0, flags=_FLAGS, stop_tokens=end_tokens)
+        # ---- accepted counts, corrected token, zeroed tail, finished flags (:300-336): one launch, no read-back
+        ops.batch_writeback(res, generated, step, g, finished, n_acc, end_tokens, n_active)
+        if not un.injected:
+            dev_off.add_(1)
+            steps_run += 1
+            n_active_host.copy_(n_active, non_blocking=True)
+            poll_event = torch.cuda.Event()
+            poll_event.record()
         step += g
+    if not un.injected:
+        un.offset += steps_run
 
     outs: List[torch.Tensor] = []
     rates: List[float] = []

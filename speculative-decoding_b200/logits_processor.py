@@ -16,7 +16,7 @@ import torch
 from torch import Tensor
 
 from . import ops
-from .uniforms import PhiloxUniforms
+from .uniforms import PhiloxUniforms, default_uniforms  # noqa: F401
 
 
 class LogitsProcessor(abc.ABC):
@@ -28,7 +28,7 @@ class LogitsProcessor(abc.ABC):
 
     def __init__(self, temperature: float):
         self.temperature = temperature
-        self.uniforms = PhiloxUniforms()
+        self.uniforms = None  # None: the process-wide default generator (uniforms.default_uniforms)
 
     def __call__(self, logits: Tensor) -> Tensor:
         probs, _ = ops.process_probs(logits, self.temperature, self.top_k, self.top_p)
@@ -46,7 +46,8 @@ class LogitsProcessor(abc.ABC):
             tok = ops.sample_probs(probs, None, greedy=True)
         else:
             rows = probs.numel() // probs.shape[-1]
-            u, _ = ops.philox_uniform(self.uniforms.seed, self.uniforms.next_offset(), 0, rows, 1, probs.device)
+            un = self.uniforms if self.uniforms is not None else default_uniforms()
+            _, u = ops.philox_uniform(un.seed, un.next_offset(), 0, rows, 1, probs.device)  # the sample lane
             tok = ops.sample_probs(probs, u.reshape(-1), greedy=False)
         return tok.reshape(*shp, 1) if len(shp) else tok.reshape(1)
 

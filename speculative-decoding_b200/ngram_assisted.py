@@ -13,7 +13,7 @@ from . import ops
 from .caching import prune_cache
 from .logits_processor import LogitsProcessor, GreedyProcessor
 from .ngram_storage import INgramStorage
-from .uniforms import PhiloxUniforms
+from .uniforms import PhiloxUniforms, default_uniforms  # noqa: F401
 
 
 @torch.no_grad()
@@ -38,7 +38,7 @@ def ngram_assisted_speculative_generate(
     if logits_processor is None:
         logits_processor = GreedyProcessor()
     fp = logits_processor.fused_params()
-    un = uniforms if uniforms is not None else PhiloxUniforms()
+    un = uniforms if uniforms is not None else default_uniforms()
     dev = target.device
     target_cache = None
     list_tokens_id = eos_tokens_id if isinstance(eos_tokens_id, list) else [eos_tokens_id]
@@ -60,10 +60,6 @@ def ngram_assisted_speculative_generate(
             u = None if fp["greedy"] else un.sample(1)
             return ops.sample_rows(row, u, **fp)[0]
         return ops.sample_rows(row, None, seed=un.seed, offset=un.next_offset(), **fp)[0]
-
-    def _probs_topk(row, k):
-        probs, _ = ops.process_probs(row, fp["temperature"], fp["top_k"], fp["top_p"])
-        return probs.reshape(-1).topk(k).indices
 
     if first_target:
         Mp = target(input_ids=input_ids[..., :current_position], past_key_values=target_cache, use_cache=use_cache)
@@ -114,7 +110,11 @@ def ngram_assisted_speculative_generate(
         else:
             res = ops.fused_verify(tl, None, toks, None, None, seed=un.seed, offset=un.next_offset(),
                                    flags=ops.L.NGRAM, stop_tokens=stop_tokens, **fp)
-        n, x, fs = int(res.n_accepted[0]), int(res.next_token[0]), int(res.first_stop[0])
+        # filler ids of every position of the step in one launch, issued BEFORE the (single) host read-back so that it
+        # runs while the host waits: ids of the filler_top_k largest logits per row (ngram_assisted.py:149-155)
+        fill = ops.topk_ids(tl[0], filler_top_k) if filler_top_k > 1 else None
+        hn, hx, hf = res.host()
+        n, x, fs = hn[0], hx[0], hf[0]
         drafts_accepted += n
         if fs >= 0:
             return copied[0, prompt_len:current_position + fs + 1].tolist(), drafts_accepted / drafts_speculated
@@ -127,11 +127,10 @@ def ngram_assisted_speculative_generate(
         for i in range(n):
             ngramstorage.update(input_ids[..., :current_position + i], input_ids[..., current_position + i].reshape(1, 1))
             if filler_top_k > 1:
-                ngramstorage.update(input_ids[..., :current_position + i],
-                                    _probs_topk(tl[:, i, :], filler_top_k).reshape(1, -1))
+                ngramstorage.update(input_ids[..., :current_position + i], fill[i].reshape(1, -1))
         ngramstorage.update(input_ids[..., :current_position + n], torch.tensor([[x]], device=dev))
         if filler_top_k > 1:
-            ngramstorage.update(input_ids[..., :current_position + n], _probs_topk(tl[:, n, :], filler_top_k).reshape(1, -1))
+            ngramstorage.update(input_ids[..., :current_position + n], fill[n].reshape(1, -1))
 
         current_position += n + 1
         if x in stop_set:

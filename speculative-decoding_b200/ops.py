@@ -119,7 +119,7 @@ def _verify_impl(target_logits: Tensor, draft_logits: Optional[Tensor], draft_to
         p_tok.data_ptr() if g else None, q_tok.data_ptr() if g else None, fstop.data_ptr(),
         nprob.data_ptr(), packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
     L.check(rc, "specdec_verify")
-    return [n_acc, nxt, mask, p_tok, q_tok, fstop, nprob, packed]
+    return [n_acc, nxt, mask, p_tok, q_tok, fstop, nprob, packed, buf]
 
 
 @torch.library.custom_op("specdec::verify", mutates_args=())
@@ -129,7 +129,7 @@ def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_token
               stop_tokens: Optional[Tensor]) -> List[Tensor]:
     # custom ops may not return views of one buffer: clone the (tiny) outputs
     return [t.clone() for t in _verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, seed, offset,
-                                            seq_id0, temperature, top_k, top_p, sample_mode, flags, stop_tokens)]
+                                            seq_id0, temperature, top_k, top_p, sample_mode, flags, stop_tokens)[:8]]
 
 
 @verify_op.register_fake
@@ -264,17 +264,75 @@ def kv_pointer_table(tensors) -> Tensor:
     return torch.tensor([t.data_ptr() for t in tensors], dtype=torch.int64, device=tensors[0].device)
 
 
+def topk_ids(logits: Tensor, k: int) -> Tensor:
+    """[..., V] logits -> [..., k] int64 ids of the k largest (value desc, index asc): the n-gram filler tokens
+    (ngram_assisted/ngram_assisted.py:149-155) without a V-wide probability row."""
+    _need_cuda(logits)
+    x, rows, V, stride = _rows_view(logits)
+    out = torch.empty((rows, int(k)), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = L.lib().specdec_topk_ids(_ptr(x), _dtype_code(x), rows, V, stride, int(k), _ptr(out), _stream())
+    L.check(rc, "specdec_topk_ids")
+    return out.reshape(*logits.shape[:-1], int(k))
+
+
+def batch_writeback(res, generated: Tensor, step, g: int, finished: Tensor, n_acc: Tensor, end_tokens: Optional[Tensor],
+                    n_active: Optional[Tensor] = None) -> None:
+    """engine/infer_engine.py:300-336 on device-resident state (see include/specdec_b200.h).  generated [B, G] int64
+    (row stride arbitrary), finished [B] uint8/bool, n_acc [B] int64, step: int or 1-element int64 CUDA tensor."""
+    _need_cuda(generated, finished, n_acc, end_tokens, n_active)
+    B = generated.shape[0]
+    if generated.dtype != torch.int64 or generated.stride(1) != 1 or n_acc.dtype != torch.int64:
+        raise ValueError("batch_writeback: generated / n_acc must be int64, generated contiguous along the step axis")
+    fin = finished.view(torch.uint8) if finished.dtype == torch.bool else finished
+    n_end = 0 if end_tokens is None else end_tokens.numel()
+    step_dev, step_host = (step.data_ptr(), 0) if isinstance(step, Tensor) else (None, int(step))
+    with torch.cuda.device(generated.device):
+        rc = L.lib().specdec_batch_writeback(B, int(g), _ptr(res.n_accepted), _ptr(res.first_stop), _ptr(res.next_token),
+                                             _ptr(generated), generated.stride(0), step_dev, step_host, _ptr(fin),
+                                             _ptr(n_acc), _ptr(end_tokens) if n_end else None, n_end, _ptr(n_active),
+                                             _stream())
+    L.check(rc, "specdec_batch_writeback")
+
+
 # ---- convenient python wrappers -------------------------------------------------------------
 class VerifyResult:
-    __slots__ = ("n_accepted", "next_token", "accept_mask", "p_tok", "q_tok", "first_stop", "next_prob", "packed")
+    __slots__ = ("n_accepted", "next_token", "accept_mask", "p_tok", "q_tok", "first_stop", "next_prob", "packed", "_buf")
 
     def __init__(self, outs):
         (self.n_accepted, self.next_token, self.accept_mask, self.p_tok, self.q_tok, self.first_stop,
-         self.next_prob, self.packed) = outs
+         self.next_prob, self.packed) = outs[:8]
+        self._buf = outs[8] if len(outs) > 8 else None
+
+    def host(self):
+        """ONE device->host copy (one sync) of everything a decode loop reads per step:
+        -> (n_accepted [B], next_token [B], first_stop [B]) as python lists.  The reference pays three `.item()` syncs
+        here (sampling/speculative_decoding.py:141-152, 172-187)."""
+        B = self.n_accepted.numel()
+        if self._buf is None:
+            return self.n_accepted.tolist(), self.next_token.tolist(), self.first_stop.tolist()
+        h = self._buf.cpu()
+        g = self.accept_mask.shape[1] if self.accept_mask.dim() == 2 else 0
+        n32 = 3 * B + 2 * B * g + B * (g + 2)
+        n32 += n32 & 1
+        i32 = h[:n32 * 4].view(torch.int32)
+        nxt = h[n32 * 4:n32 * 4 + B * 8].view(torch.int64)
+        return i32[0:B].tolist(), nxt.tolist(), i32[B:2 * B].tolist()
+
+
+def _device_offset(offset, dev):
+    """offset given as a 1-element int64 CUDA tensor -> its address (the kernels read the word when they run)."""
+    if offset.device != dev or offset.dtype != torch.int64 or offset.numel() != 1:
+        raise ValueError("a device-resident Philox offset must be a 1-element int64 tensor on the logits' device")
+    return offset.data_ptr()
 
 
 def fused_verify(target_logits, draft_logits, draft_tokens, u_accept=None, u_sample=None, *, seed=0, offset=0,
                  seq_id0=0, temperature=1.0, top_k=0, top_p=1.0, greedy=False, flags=0, stop_tokens=None) -> VerifyResult:
+    """offset: int, or a 1-element int64 CUDA tensor (device-resident step counter: a captured CUDA graph of the step
+    draws fresh uniforms on every replay once the caller bumps the tensor, e.g. `offset.add_(1)` inside the graph)."""
+    if isinstance(offset, Tensor):
+        offset, flags = _device_offset(offset, target_logits.device), int(flags) | L.OFFSET_DEVICE
     if stop_tokens is not None and not isinstance(stop_tokens, Tensor):
         stop_tokens = torch.as_tensor(list(stop_tokens), dtype=torch.int64, device=target_logits.device)
     if stop_tokens is not None and stop_tokens.numel() == 0:
@@ -292,6 +350,8 @@ def process_probs(logits, temperature=1.0, top_k=0, top_p=1.0):
 
 def sample_rows(logits, u=None, *, seed=0, offset=0, seq_id0=0, lane_id=0, temperature=1.0, top_k=0, top_p=1.0,
                 greedy=False):
+    if isinstance(offset, Tensor):
+        offset, lane_id = _device_offset(offset, logits.device), int(lane_id) | L.LANE_OFFSET_DEVICE
     return sample_rows_op(logits, u, int(seed), int(offset), int(seq_id0), int(lane_id), float(temperature),
                           int(top_k), float(top_p), L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF)
 

@@ -15,7 +15,7 @@ from torch.nn import Module
 from . import ops
 from .caching import prune_cache
 from .logits_processor import LogitsProcessor, GreedyProcessor
-from .uniforms import PhiloxUniforms
+from .uniforms import PhiloxUniforms, default_uniforms  # noqa: F401
 
 
 def max_fn(x: torch.Tensor) -> torch.Tensor:
@@ -49,7 +49,7 @@ def speculative_generate(
     if logits_processor is None:
         logits_processor = GreedyProcessor()
     fp = logits_processor.fused_params()
-    un = uniforms if uniforms is not None else PhiloxUniforms()
+    un = uniforms if uniforms is not None else default_uniforms()
     dev = target.device
     drafter_cache, target_cache = None, None
 
@@ -119,7 +119,8 @@ def speculative_generate(
             res = ops.fused_verify(tl, dl, toks, None, None, seed=un.seed, offset=un.next_offset(), flags=flags,
                                    stop_tokens=stop_tokens, **fp)
         # one host sync per step
-        n, x, fs = int(res.n_accepted[0]), int(res.next_token[0]), int(res.first_stop[0])
+        hn, hx, hf = res.host()
+        n, x, fs = hn[0], hx[0], hf[0]
         drafts_accepted += n
 
         if fs >= 0:  # an accepted draft is a stop token (sampling/speculative_decoding.py:150-155)

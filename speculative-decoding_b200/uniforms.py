@@ -25,6 +25,22 @@ class PhiloxUniforms:
         return o
 
 
+_DEFAULT = None
+
+
+def default_uniforms() -> PhiloxUniforms:
+    """The process-wide generator every API call without an explicit `uniforms` draws from: keyed by
+    torch.initial_seed() (re-keyed, offset 0, when the user reseeds with torch.manual_seed) and with an offset that
+    PERSISTS across calls -- like the reference's global torch generator, successive speculative_generate /
+    LogitsProcessor.sample / batch calls never replay one another's uniforms.  Every consumer takes a fresh offset per
+    kernel call, so two calls never share a (seed, offset) pair whatever Philox lane they read."""
+    global _DEFAULT
+    seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+    if _DEFAULT is None or _DEFAULT.seed != seed:
+        _DEFAULT = PhiloxUniforms(seed)
+    return _DEFAULT
+
+
 class InjectedUniforms:
     """sample_u feeds every sample() call, accept_u feeds the rand(gamma) of the accept test."""
     injected = True

@@ -174,3 +174,132 @@ def test_missing_library_fails_loudly(monkeypatch):
     with pytest.raises(RuntimeError, match="CUDA tensors only"):
         sd.ops.verify_op(torch.zeros(1, 2, 8), torch.zeros(1, 1, 8), torch.zeros(1, 1, dtype=torch.long), None, None,
                          0, 0, 0, 1.0, 0, 1.0, 1, 0, None)
+
+
+# ---- decode-loop helpers (csrc/engine.cu), device-resident Philox offset, default generator ----
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32, torch.float16])
+@pytest.mark.parametrize("V,k", [(32000, 3), (128256, 3), (1000, 8), (5003, 11), (7, 7)])
+def test_topk_ids_matches_stable_sort(dtype, V, k):
+    """ngram_assisted/ngram_assisted.py:149-155: torch.topk(p, filler_top_k).indices; our order is value desc / index asc."""
+    import specdec_b200 as sd
+    g = torch.Generator().manual_seed(V + k)
+    z = (3 * torch.randn(5, V, generator=g)).to(dtype)
+    z[1, : V // 2] = z[1, 0]          # a large tie group
+    z[2, V - 1] = 100.0               # maximum at the ragged end
+    z[3] = float("-inf"); z[3, V // 3] = 0.5
+    ids = sd.ops.topk_ids(z.cuda(), k).cpu()
+    want = torch.sort(z.float(), dim=-1, descending=True, stable=True).indices[:, :k]
+    assert torch.equal(ids, want)
+    # strided view of a [B, L, V] model output
+    big = torch.zeros(5, 3, V, dtype=dtype); big[:, 1] = z
+    assert torch.equal(sd.ops.topk_ids(big.cuda()[:, 1], k).cpu(), want)
+
+
+def _writeback_torch(generated, step, g, n, fs, x, finished, n_acc, end_tokens):
+    """the vectorised torch statement of engine/infer_engine.py:300-336 this kernel replaced"""
+    device = generated.device
+    active = ~finished
+    n, fs = n.long(), fs.long()
+    hit_end = fs >= 0
+    acc_cnt = torch.where(hit_end, fs + 1, n)
+    rejected = (~hit_end) & (n < g)
+    n_acc = n_acc + torch.where(active, acc_cnt, torch.zeros_like(acc_cnt))
+    ar = torch.arange(g, device=device)
+    cur = generated[:, step:step + g]
+    corr = rejected.unsqueeze(1) & (ar.unsqueeze(0) == n.unsqueeze(1))
+    cur = torch.where(corr, x.unsqueeze(1), cur)
+    tail = (acc_cnt < g).unsqueeze(1) & (ar.unsqueeze(0) >= (acc_cnt + 1).unsqueeze(1))
+    cur = torch.where(tail, torch.zeros_like(cur), cur)
+    generated = generated.clone()
+    generated[:, step:step + g] = torch.where(active.unsqueeze(1), cur, generated[:, step:step + g])
+    x_is_end = torch.isin(x, end_tokens) if end_tokens.numel() else torch.zeros_like(rejected)
+    finished = finished | (active & (hit_end | (rejected & x_is_end)))
+    return generated, finished, n_acc
+
+
+@pytest.mark.parametrize("step_on_device", [False, True])
+def test_batch_writeback_matches_torch_statement(step_on_device):
+    import specdec_b200 as sd
+    gen = torch.Generator().manual_seed(5)
+    B, G, g, step = 300, 24, 6, 12
+    generated = torch.randint(1, 1000, (B, G), generator=gen).cuda()
+    n = torch.randint(0, g + 1, (B,), generator=gen).int().cuda()
+    fs = torch.where(torch.rand(B, generator=gen) < 0.2, torch.randint(0, g, (B,), generator=gen), torch.full((B,), -1)).int().cuda()
+    fs = torch.where(fs >= n, torch.full_like(fs, -1), fs)  # a stop can only sit among the accepted drafts
+    x = torch.randint(0, 20, (B,), generator=gen).cuda()
+    finished = (torch.rand(B, generator=gen) < 0.3).cuda()
+    n_acc = torch.randint(0, 50, (B,), generator=gen).cuda()
+    end_tokens = torch.tensor([3, 7], dtype=torch.long).cuda()
+
+    class R:
+        pass
+    r = R(); r.n_accepted, r.first_stop, r.next_token = n, fs, x
+    wg, wf, wa = _writeback_torch(generated, step, g, n, fs, x, finished, n_acc, end_tokens)
+    g2, f2, a2 = generated.clone(), finished.clone(), n_acc.clone()
+    n_active = torch.full((1,), -5, dtype=torch.int32).cuda()
+    st = torch.tensor([step], dtype=torch.int64).cuda() if step_on_device else step
+    sd.ops.batch_writeback(r, g2, st, g, f2, a2, end_tokens, n_active)
+    assert torch.equal(g2, wg) and torch.equal(f2, wf) and torch.equal(a2, wa)
+    assert int(n_active[0]) == int((~wf).sum())
+
+
+def test_device_resident_offset_equals_host_offset_and_advances_in_a_graph(oracle_mod):
+    import specdec_b200 as sd
+    case = make_case(B=6, gamma=4, V=32000, dtype="bf16", sigma=0.5, seed=3, oracle=oracle_mod, mode="multinomial")
+    t, d, tk = case["target"].cuda(), case["draft"].cuda(), case["draft_tokens"].cuda()
+    off = torch.zeros(1, dtype=torch.int64).cuda()
+    host = [sd.fused_verify(t, d, tk, None, None, seed=99, offset=i) for i in range(4)]
+    for i in range(4):
+        off.fill_(i)
+        r = sd.fused_verify(t, d, tk, None, None, seed=99, offset=off)
+        assert torch.equal(r.packed, host[i].packed) and torch.equal(r.accept_mask, host[i].accept_mask)
+        z = d.reshape(-1, 32000)
+        a, _ = sd.sample_rows(z, None, seed=99, offset=off, lane_id=2)
+        b, _ = sd.sample_rows(z, None, seed=99, offset=i, lane_id=2)
+        assert torch.equal(a, b)
+    # one captured step, replayed: the device word advances inside the graph, the uniforms with it
+    off.fill_(0)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        sd.fused_verify(t, d, tk, None, None, seed=99, offset=off)
+    torch.cuda.current_stream().wait_stream(side)
+    gph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gph):
+        rg = sd.fused_verify(t, d, tk, None, None, seed=99, offset=off)
+        off.add_(1)
+    for i in range(4):
+        gph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(rg.packed, host[i].packed), i
+    assert int(off[0]) == 4
+    assert any(not torch.equal(host[0].packed, host[i].packed) for i in range(1, 4))
+
+
+def test_default_uniforms_advance_across_calls_and_rekey_on_manual_seed():
+    import specdec_b200 as sd
+    from specdec_b200 import uniforms as _u
+    _u._DEFAULT = None
+    torch.manual_seed(1234)
+    un = sd.default_uniforms()
+    assert un.offset == 0 and un is sd.default_uniforms()
+    p = torch.softmax(torch.randn(64, 500, generator=torch.Generator().manual_seed(0)), -1).cuda()
+    proc = sd.MultinomialProcessor(1.0)
+    a = proc.sample(p)
+    b = proc.sample(p)
+    assert un.offset == 2 and not torch.equal(a, b), "successive calls must not replay the same uniforms"
+    proc2 = sd.NucleusProcessor(1.0, 0.9)   # another processor instance shares the generator
+    proc2.sample(p)
+    assert un.offset == 3
+    torch.manual_seed(77)                   # re-keyed by the user: new stream, offset 0
+    un2 = sd.default_uniforms()
+    assert un2 is not un and un2.offset == 0 and un2.seed == 77
+
+
+def test_verify_result_host_is_one_copy(oracle_mod):
+    import specdec_b200 as sd
+    case = make_case(B=5, gamma=3, V=5000, dtype="f32", sigma=0.5, seed=11, oracle=oracle_mod, mode="multinomial")
+    r = sd.fused_verify(case["target"].cuda(), case["draft"].cuda(), case["draft_tokens"].cuda(), None, None, seed=5,
+                        stop_tokens=[int(case["draft_tokens"][0, 0])])
+    n, x, fs = r.host()
+    assert n == r.n_accepted.tolist() and x == r.next_token.tolist() and fs == r.first_stop.tolist()
