@@ -168,8 +168,9 @@ SPECDEC_API int specdec_prune_kv(void* const* tensor_ptrs, int n_tensors, int B,
  * Device n-gram tables: NGramStorage / OneLevelNGramStorage (ngram_assisted/ngram_storage.py:73-249).
  * One logical table per table id (sequence); capacity is per table.  `one_level`!=0 gives
  * OneLevelNGramStorage semantics (single context length n-1).
- * The handle is a host pointer; table memory is allocated once at create (cudaMalloc) -- the
- * only allocation in the library, mirroring the reference's constructor.
+ * The handle is a host pointer; table memory is allocated once at create (cudaMalloc), mirroring the
+ * reference's constructor; create returns after the tables are zeroed (it synchronises the NULL stream).
+ * table_ids must lie in [0, n_tables): the kernels index the tables with them unchecked (the Python host validates).
  */
 typedef struct specdec_ngram specdec_ngram_t;
 SPECDEC_API int specdec_ngram_create(specdec_ngram_t** out, int n, int vocab_size, int n_tables, int grams_per_table,
@@ -187,6 +188,13 @@ SPECDEC_API int specdec_ngram_update(specdec_ngram_t* t, const int64_t* ids, con
 SPECDEC_API int specdec_ngram_lookup_chain(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids,
                                int B, int64_t max_len, int gamma, const int64_t* fallback, int64_t* drafts,
                                uint8_t* known, specdec_stream_t stream);
+/* has_gram (ngram_storage.py:98-106 / :181-193), exact: out[b] = 1 iff the final token of row b was ever counted after
+ * the context made of the row's last j tokens (the reference's context includes that final token), longest j first. */
+SPECDEC_API int specdec_ngram_has_gram(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids,
+                           int B, int64_t max_len, uint8_t* out, specdec_stream_t stream);
+/* seed of the fallback tokens lookup_chain draws ON THE DEVICE for unknown contexts when `fallback` is NULL
+ * (Philox keyed by seed, call number, sequence, position; the reference draws torch.randint, ngram_storage.py:84,165) */
+SPECDEC_API int specdec_ngram_seed(specdec_ngram_t* t, uint64_t seed);
 /* device int32[2]: {overflow flag, entries used (max over tables)} */
 SPECDEC_API int specdec_ngram_status(specdec_ngram_t* t, int32_t* host_out2);
 

@@ -73,6 +73,24 @@ class NGramOracle:
                 return b[j][g], True
         return fallback, False
 
+    def has_gram(self, ngram, tab=0):
+        """ngram_storage.py:98-106 (one level) / :181-193: the context is the LAST j tokens of `ngram`, its final token
+        included, and the question is whether that final token was ever counted after it."""
+        ngram = [int(t) for t in ngram]
+        c = self.counts.get(tab, {})
+        if self.one_level:
+            if len(ngram) < self.n:
+                return False
+            g = tuple(ngram[-(self.n - 1):])
+            return g in c.get(self.n - 1, {}) and ngram[-1] in c[self.n - 1][g]
+        if len(ngram) < 1:
+            return False
+        for j in range(min(self.n - 1, len(ngram)), 1, -1):
+            g = tuple(ngram[-j:])
+            if g in c.get(j, {}) and ngram[-1] in c[j][g]:
+                return True
+        return False
+
     def lookup_chain(self, seqs, gamma, table_ids=None, fallback=None):
         drafts, known = [], []
         for i, seq in enumerate(seqs):

@@ -12,7 +12,9 @@
 //      partial sums from the weights cached in shared memory, token location -- one launch.
 //   3'/4'. exact_rows_kernel + sample_partial_kernel: the same work as two launches without the cache
 //      (fallback for huge vocabularies, test hook "no_fused_tail"; sample_partial also serves the masked
-//      modes).  Tails are chained with "last CTA done" counters (no host sync, no spin).
+//      modes).  Their tails are chained with "last CTA done" counters (no host sync, no spin); the fused tail's
+//      CTAs of one sequence DO wait for one another (bounded, ticket-ordered: tail_fused.cuh) and the launcher falls
+//      back to this pair whenever fewer CTAs than one sequence needs can be co-resident.
 //
 // top-k / nucleus modes use the exact rowstats_kernel for every row (their kept sets need exact
 // masses) followed by plan_kernel (no tasks).  Outputs are bit-identical to the exact-everywhere path.

@@ -10,6 +10,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include "../../include/specdec_b200.h"
+#include "canon.cuh"  // philox_word0 (fallback tokens of unknown contexts)
 
 #define NG_MAXCTX 8
 
@@ -32,6 +33,7 @@ struct specdec_ngram {
   CountSlot* counts;
   int* status;  // [0] overflow flag, [1] max grams used
   int* used;    // per table gram count
+  unsigned long long seed, calls;  // fallback tokens of unknown contexts: Philox(seed; call number, sequence, position)
 };
 
 namespace specdec {
@@ -127,42 +129,103 @@ __global__ void ngram_write_kernel(specdec_ngram t, const long long* ids, const 
   atomicMax(&t.status[1], *used);
 }
 
-// gamma chained lookups per sequence (ngram_assisted.py:95-99 -> ngram_storage.py:164-179 / :83-96)
-__global__ void ngram_lookup_kernel(specdec_ngram t, const long long* ids, const int* lens, const int* table_ids,
-                                    int B, long long max_len, int gamma, const long long* fallback,
-                                    long long* drafts, unsigned char* known) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+// read-only probe of the (gram, token) count table: the count, 0 if never seen
+__device__ int ng_count(const CountSlot* c, int C, int gram, int tok) {
+  unsigned h = ((unsigned)gram * 2654435761u ^ (unsigned)tok * 40503u) % (unsigned)C;
+  for (int probe = 0; probe < C; ++probe) {
+    const CountSlot& s = c[h];
+    if (s.gram == 0) return 0;
+    if (s.gram == gram + 1 && s.tok == tok) return s.cnt;
+    h = (h + 1 == (unsigned)C) ? 0u : h + 1;
+  }
+  return 0;
+}
+
+// gamma chained lookups per sequence (ngram_assisted.py:95-99 -> ngram_storage.py:164-179 / :83-96).
+// One WARP per sequence: lane j probes context length j, so the back-off levels of one next_token() call are looked up
+// side by side (their hash probes are dependent global loads: the chain of gamma calls is latency bound) and the
+// longest hit wins -- the order the reference's `for j in range(min(n-1, len), 1, -1)` loop tries them in.
+__global__ void __launch_bounds__(128) ngram_lookup_kernel(specdec_ngram t, const long long* ids, const int* lens, const int* table_ids,
+                                                           int B, long long max_len, int gamma, const long long* fallback,
+                                                           long long* drafts, unsigned char* known) {
+  __shared__ long long s_win[4][NG_MAXCTX + 64];  // last n-1 real tokens followed by the drafts made so far
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * 4 + wib;
   if (b >= B) return;
   const int tab = table_ids ? table_ids[b] : 0;
   const GramSlot* g = t.grams + (size_t)tab * t.G;
   const long long* seq = ids + (size_t)b * max_len;
   const int len0 = lens[b];
-  long long win[NG_MAXCTX + 64];  // last n-1 real tokens followed by the drafts made so far
+  long long* win = s_win[wib];
   const int keep = min(t.n - 1, len0);
-  for (int i = 0; i < keep; ++i) win[i] = seq[len0 - keep + i];
+  if (lane < keep) win[lane] = seq[len0 - keep + lane];
+  __syncwarp();
   int wl = keep;
   for (int k = 0; k < gamma; ++k) {
     const int len = len0 + k;
-    long long out = fallback ? fallback[(size_t)b * gamma + k] : 0;
+    int dummy = 0, gi = -1;
+    const int jmax = min(t.n - 1, len);
+    const bool mine = t.one_level ? (lane == t.n - 1 && len >= t.n - 1) : (lane >= 2 && lane <= jmax);
+    if (mine) gi = ng_find_gram((GramSlot*)g, t.G, win + wl - lane, lane, 0, &dummy);
+    const unsigned hits = __ballot_sync(0xffffffffu, gi >= 0);
+    long long out;
     unsigned char kn = 0;
-    int dummy = 0;
-    if (t.one_level) {
-      if (len >= t.n - 1) {
-        const int gi = ng_find_gram((GramSlot*)g, t.G, win + wl - (t.n - 1), t.n - 1, 0, &dummy);
-        if (gi >= 0) { out = g[gi].best_tok; kn = 1; }
-      }
-    } else {
-      for (int j = min(t.n - 1, len); j > 1; --j) {
-        const int gi = ng_find_gram((GramSlot*)g, t.G, win + wl - j, j, 0, &dummy);
-        if (gi >= 0) { out = g[gi].best_tok; kn = 1; break; }
-      }
+    if (hits) {
+      const int src = 31 - __clz(hits);  // longest context that is known
+      const int bt = (gi >= 0) ? g[gi].best_tok : 0;
+      out = (long long)__shfl_sync(0xffffffffu, bt, src);
+      kn = 1;
+    } else if (fallback) {
+      out = fallback[(size_t)b * gamma + k];
+    } else {  // the reference draws torch.randint(vocab_size) (ngram_storage.py:84,165)
+      out = (long long)(philox_word0(t.seed, t.calls, (unsigned)b, (unsigned)k) % (unsigned)t.vocab);
     }
-    drafts[(size_t)b * gamma + k] = out;
-    known[(size_t)b * gamma + k] = kn;
+    if (lane == 0) {
+      drafts[(size_t)b * gamma + k] = out;
+      known[(size_t)b * gamma + k] = kn;
+    }
     // slide the window
-    if (wl == NG_MAXCTX + 63) { for (int i = 1; i < wl; ++i) win[i - 1] = win[i]; --wl; }
-    win[wl++] = out;
+    __syncwarp();
+    if (wl == NG_MAXCTX + 63) {
+      long long v = (lane + 1 < wl) ? win[lane + 1] : 0, v2 = (lane + 33 < wl) ? win[lane + 33] : 0, v3 = (lane + 65 < wl) ? win[lane + 65] : 0;
+      __syncwarp();
+      if (lane + 1 < wl) win[lane] = v;
+      if (lane + 33 < wl) win[lane + 32] = v2;
+      if (lane + 65 < wl) win[lane + 64] = v3;
+      --wl;
+      __syncwarp();
+    }
+    if (lane == 0) win[wl] = out;
+    ++wl;
+    __syncwarp();
   }
+}
+
+// has_gram (ngram_storage.py:98-106 / :181-193), exact: the reference takes the LAST j tokens of `ngram` (its final
+// token included) as the context and asks whether that same final token has ever been counted after it.
+__global__ void ngram_has_kernel(specdec_ngram t, const long long* ids, const int* lens, const int* table_ids, int B,
+                                 long long max_len, unsigned char* out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int tab = table_ids ? table_ids[b] : 0;
+  const GramSlot* g = t.grams + (size_t)tab * t.G;
+  const CountSlot* c = t.counts + (size_t)tab * t.C;
+  const long long* seq = ids + (size_t)b * max_len;
+  const int len = lens[b];
+  unsigned char res = 0;
+  int dummy = 0;
+  if (t.one_level) {
+    if (len >= t.n) {
+      const int gi = ng_find_gram((GramSlot*)g, t.G, seq + len - (t.n - 1), t.n - 1, 0, &dummy);
+      if (gi >= 0 && ng_count(c, t.C, gi, (int)seq[len - 1]) > 0) res = 1;
+    }
+  } else if (len >= 1) {
+    for (int j = min(t.n - 1, len); j > 1 && !res; --j) {
+      const int gi = ng_find_gram((GramSlot*)g, t.G, seq + len - j, j, 0, &dummy);
+      if (gi >= 0 && ng_count(c, t.C, gi, (int)seq[len - 1]) > 0) res = 1;
+    }
+  }
+  out[b] = res;
 }
 
 }  // namespace specdec
@@ -183,7 +246,22 @@ int specdec_ngram_create(specdec_ngram_t** out, int n, int vocab_size, int n_tab
   if ((e = cudaMalloc(&t->status, sizeof(int) * 2)) != cudaSuccess) { cudaFree(t->grams); cudaFree(t->counts); free(t); return (int)e; }
   if ((e = cudaMalloc(&t->used, sizeof(int) * (size_t)n_tables)) != cudaSuccess) { cudaFree(t->grams); cudaFree(t->counts); cudaFree(t->status); free(t); return (int)e; }
   *out = t;
-  return specdec_ngram_reset(t, nullptr);
+  // the tables are zero before create returns, whatever stream the caller works on afterwards
+  const int rc = specdec_ngram_reset(t, nullptr);
+  if (rc) return rc;
+  return (int)cudaStreamSynchronize(nullptr);
+}
+int specdec_ngram_seed(specdec_ngram_t* t, uint64_t seed) {
+  if (!t) return SPECDEC_ERR_ARG;
+  t->seed = seed; t->calls = 0;
+  return 0;
+}
+int specdec_ngram_has_gram(specdec_ngram_t* t, const int64_t* ids, const int32_t* lens, const int32_t* table_ids, int B,
+                           int64_t max_len, uint8_t* out, specdec_stream_t stream) {
+  if (!t || !ids || !lens || !out || B < 0) return SPECDEC_ERR_ARG;
+  if (B == 0) return 0;
+  specdec::ngram_has_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(*t, (const long long*)ids, lens, table_ids, B, max_len, out);
+  return (int)cudaGetLastError();
 }
 int specdec_ngram_destroy(specdec_ngram_t* t) {
   if (!t) return 0;
@@ -221,9 +299,10 @@ int specdec_ngram_lookup_chain(specdec_ngram_t* t, const int64_t* ids, const int
                                uint8_t* known, specdec_stream_t stream) {
   if (!t || !ids || !lens || !drafts || !known || B < 0 || gamma < 0 || gamma > 64) return SPECDEC_ERR_ARG;
   if (B == 0 || gamma == 0) return 0;
-  specdec::ngram_lookup_kernel<<<(B + 63) / 64, 64, 0, (cudaStream_t)stream>>>(
+  specdec::ngram_lookup_kernel<<<(B + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
       *t, (const long long*)ids, lens, table_ids, B, max_len, gamma, (const long long*)fallback,
       (long long*)drafts, known);
+  if (!fallback) ++t->calls;  // every call without caller-supplied fallbacks draws fresh ones
   return (int)cudaGetLastError();
 }
 int specdec_ngram_status(specdec_ngram_t* t, int32_t* host_out2) {

@@ -1827,16 +1827,32 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   const int nch = g_tf_ch;
   const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5), spc = (nseg + nch - 1) / nch;
   const size_t tf_smem = (size_t)spc * TF_SEG_BYTES;
-  if (!masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail) {
+  bool fused_ok = !masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail;
+  auto tail = dj.greedy ? tail_fused_kernel<DT, true> : tail_fused_kernel<DT, false>;
+  if (fused_ok) {
+    // The nch CTAs of a sequence wait for one another (tail_fused.cuh): that needs at least nch CTAs co-resident on
+    // the device (ticket order then guarantees progress).  Under an SM limit (MPS / green contexts) or with a huge
+    // slice the occupancy query says otherwise and the step takes the split pipeline, whose CTAs never wait.
+    static size_t attr_smem_dev[MAXDEV][2];  // dynamic shared memory already granted (per device, per instantiation)
+    static size_t occ_smem_dev[MAXDEV][2];
+    static int occ_dev[MAXDEV][2];
+    const int dv = cur_dev(), gi = dj.greedy ? 1 : 0;
+    if (attr_smem_dev[dv][gi] < tf_smem) {
+      cudaError_t e = cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem);
+      if (e != cudaSuccess) return e;
+      attr_smem_dev[dv][gi] = tf_smem;
+    }
+    if (occ_smem_dev[dv][gi] != tf_smem) {
+      int occ = 0;
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tail, TF_T, tf_smem) != cudaSuccess) occ = 0;
+      occ_dev[dv][gi] = occ;
+      occ_smem_dev[dv][gi] = tf_smem;
+    }
+    if ((long long)occ_dev[dv][gi] * num_sms() < nch) fused_ok = false;
+  }
+  if (fused_ok) {
     ws.fused = 1;
     cudaError_t e;
-    static size_t attr_smem_dev[MAXDEV][2];  // dynamic shared memory already granted (per device, per instantiation)
-    size_t* attr_smem = attr_smem_dev[cur_dev()];
-    auto tail = dj.greedy ? tail_fused_kernel<DT, true> : tail_fused_kernel<DT, false>;
-    if (attr_smem[dj.greedy ? 1 : 0] < tf_smem) {
-      if ((e = cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem)) != cudaSuccess) return e;
-      attr_smem[dj.greedy ? 1 : 0] = tf_smem;
-    }
     // programmatic dependent launches: the CTAs of plan / tail are scheduled while their predecessor drains
     cudaLaunchAttribute pdl[1];
     pdl[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

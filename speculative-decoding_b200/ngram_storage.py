@@ -6,7 +6,8 @@ Differences by design:
   * `table_ids` (optional) gives every sequence its own logical table -- the layout batched
     n-gram-assisted decoding needs; default = one shared table, as in the reference;
   * `lookup_chain` runs the gamma chained next_token() calls of ngram_assisted.py:95-99 in one launch;
-  * unknown contexts take a caller-supplied / Philox fallback token instead of torch.randint
+  * unknown contexts take a caller-supplied fallback token or one drawn ON THE DEVICE (Philox keyed by the storage's
+    seed, the call number, the sequence and the position) instead of a host torch.randint
     (ngram_storage.py:84,165); an empty table is a miss, not a KeyError (:174).
 """
 from __future__ import annotations
@@ -53,13 +54,14 @@ class _DeviceNGram(INgramStorage):
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("device n-gram tables need a CUDA device (no CPU fallback)")
+        if n - 1 > 8:
+            raise ValueError("device n-gram tables hold contexts of at most 8 tokens (n <= 9)")
         self.n_tables = n_tables
         self._h = C.c_void_p()
-        self._seed = seed
-        self._calls = 0
         with torch.cuda.device(self.device):
             L.check(L.lib().specdec_ngram_create(C.byref(self._h), n, vocab_size, n_tables, grams_per_table,
                                                  counts_per_table, self._one_level), "specdec_ngram_create")
+            L.check(L.lib().specdec_ngram_seed(self._h, int(seed) & 0xFFFFFFFFFFFFFFFF), "specdec_ngram_seed")
 
     def __del__(self):
         try:
@@ -79,6 +81,13 @@ class _DeviceNGram(INgramStorage):
         else:
             lens = lens.to(device=self.device, dtype=torch.int32).contiguous()
         if table_ids is not None:
+            # the kernels index the tables with these ids unchecked: validate once per distinct tensor (one sync),
+            # not per call
+            key = (table_ids.data_ptr(), table_ids.numel(), table_ids._version)
+            if key != getattr(self, "_tab_ok", None):
+                if table_ids.numel() != B or (table_ids.numel() and (int(table_ids.min()) < 0 or int(table_ids.max()) >= self.n_tables)):
+                    raise ValueError(f"table_ids must hold one id in [0, {self.n_tables}) per sequence")
+                self._tab_ok = key
             table_ids = table_ids.to(device=self.device, dtype=torch.int32).contiguous()
         return ids, lens, table_ids, B, ml
 
@@ -89,17 +98,11 @@ class _DeviceNGram(INgramStorage):
     def _stream(self):
         return torch.cuda.current_stream(self.device).cuda_stream
 
-    def _fallback(self, B, gamma):
-        g = torch.Generator(device="cpu").manual_seed(self._seed + self._calls)
-        self._calls += 1
-        return torch.randint(self.vocab_size, (B, gamma), generator=g).to(self.device)
-
     # -- INgramStorage
     def lookup_chain(self, input_ids, gamma: int, lens=None, table_ids=None, fallback=None):
         ids, lens, table_ids, B, ml = self._prep(input_ids, lens, table_ids)
-        if fallback is None:
-            fallback = self._fallback(B, gamma)
-        fallback = fallback.to(device=self.device, dtype=torch.int64).reshape(B, gamma).contiguous()
+        if fallback is not None:  # None: drawn on the device (no host RNG, no copy)
+            fallback = fallback.to(device=self.device, dtype=torch.int64).reshape(B, gamma).contiguous()
         drafts = torch.empty((B, gamma), dtype=torch.int64, device=self.device)
         known = torch.empty((B, gamma), dtype=torch.uint8, device=self.device)
         with torch.cuda.device(self.device):
@@ -129,14 +132,18 @@ class _DeviceNGram(INgramStorage):
         with torch.cuda.device(self.device):
             L.check(L.lib().specdec_ngram_reset(self._h, self._stream()), "specdec_ngram_reset")
 
-    def has_gram(self, ngram: torch.Tensor) -> bool:
-        """True iff the last token of `ngram` has been seen after its preceding context
-        (ngram_storage.py:98-106 / :181-193).  Implemented by probing best tokens is not enough, so the
-        check replays the lookup on the context and compares: exact for the arg-max token only."""
-        if ngram.shape[0] < 2:
+    def has_gram(self, ngram: torch.Tensor, table_id: int = 0) -> bool:
+        """ngram_storage.py:98-106 / :181-193, exact (a probe of the gram and count tables, no insert): True iff the
+        final token of `ngram` was ever counted after the context made of its last j tokens."""
+        if ngram.numel() < 1:
             return False
-        tok, known = self.next_token(ngram[:-1].reshape(1, -1))
-        return bool(known[0]) and int(tok[0]) == int(ngram[-1])
+        tabs = None if self.n_tables == 1 else torch.tensor([table_id], dtype=torch.int32, device=self.device)
+        ids, lens, tabs, B, ml = self._prep(ngram.reshape(1, -1), None, tabs)
+        out = torch.empty(1, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            L.check(L.lib().specdec_ngram_has_gram(self._h, self._p(ids), self._p(lens), self._p(tabs), 1, ml, self._p(out),
+                                                   self._stream()), "specdec_ngram_has_gram")
+        return bool(out[0])
 
     def status(self):
         out = (C.c_int32 * 2)()

@@ -159,10 +159,37 @@ def test_ngram_tables_match_oracle(one_level):
             od, ok = orc.lookup_chain([seqs[i, :lens[i]] for i in range(B)], 5, None if tabs is None else tabs.tolist(), fb)
             assert d.cpu().tolist() == od and k.cpu().tolist() == ok
             lens = np.maximum(lens - (step % 2), 0).astype(np.int32)
+        # has_gram: exact (every counted token, not only the arg-max one), ngram_storage.py:98-106 / :181-193
+        for trial in range(60):
+            L_ = int(rng.randint(1, 8))
+            q = rng.randint(0, 6, size=L_)
+            tb = int(rng.randint(0, B)) if per_seq else 0
+            assert st.has_gram(torch.from_numpy(q), tb) == orc.has_gram(q, tb), (q, tb)
         assert not st.status()["overflow"]
         st.reset()
         d, k = st.lookup_chain(ids, 2, torch.from_numpy(lens), tabs, torch.zeros(B, 2, dtype=torch.long))
         assert not bool(k.any())
+
+
+def test_ngram_device_fallback_tokens_and_table_id_validation():
+    import specdec_b200 as sd
+    V, B = 1000, 16
+    ids = torch.randint(0, 50, (B, 12), generator=torch.Generator().manual_seed(0))
+    outs = []
+    for seed in (5, 5, 6):
+        st = sd.NGramStorage(4, V, n_tables=B, grams_per_table=256, counts_per_table=512, seed=seed)
+        tabs = torch.arange(B, dtype=torch.int32)
+        d1, k1 = st.lookup_chain(ids, 4, table_ids=tabs)   # empty tables: everything is a fallback token
+        d2, k2 = st.lookup_chain(ids, 4, table_ids=tabs)
+        assert not bool(k1.any()) and int(d1.min()) >= 0 and int(d1.max()) < V
+        assert not torch.equal(d1, d2), "every call draws fresh fallback tokens"
+        outs.append(d1.cpu())
+    assert torch.equal(outs[0], outs[1]) and not torch.equal(outs[0], outs[2])
+    st = sd.NGramStorage(4, V, n_tables=4)
+    with pytest.raises(ValueError):
+        st.lookup_chain(ids, 2, table_ids=torch.arange(B, dtype=torch.int32))  # ids 4..15 are out of range
+    with pytest.raises(ValueError):
+        sd.NGramStorage(11, V)
 
 
 def test_missing_library_fails_loudly(monkeypatch):

@@ -66,3 +66,29 @@ def test_oracle_accept_decisions_match_reference_arithmetic(oracle_mod):
             n, _ = torch_port.verify_one(case["target"][b], case["draft"][b], case["draft_tokens"][b], m,
                                          r=case["u_accept"][b])
             assert n == o.n_accepted[b], (mode, b)
+
+
+@pytest.mark.parametrize("one_level", [False, True])
+def test_ngram_oracle_has_gram_matches_reference_classes(one_level):
+    """ngram_storage.py:98-106 / :181-193 on the real classes vs oracle/ngram_oracle.py:has_gram."""
+    from oracle.ngram_oracle import NGramOracle
+    ng = rh.ref_modules().ng
+    import ngram_assisted.ngram_storage as ns
+    rng = np.random.RandomState(3)
+    n, V = 4, 50
+    ref = (ns.OneLevelNGramStorage if one_level else ns.NGramStorage)(n, V)
+    orc = NGramOracle(n, V, one_level)
+    seq = rng.randint(0, 5, size=(1, 40))
+    ref.initialize(torch.from_numpy(seq))
+    orc.initialize([seq[0]])
+    for step in range(6):
+        nt = rng.randint(0, 5, size=(1, 2))
+        ref.update(torch.from_numpy(seq[:, :30 + step]), torch.from_numpy(nt))
+        orc.update([seq[0, :30 + step]], nt)
+    for trial in range(300):
+        q = rng.randint(0, 5, size=int(rng.randint(1, 8)))
+        try:
+            want = bool(ref.has_gram(torch.from_numpy(q)))
+        except KeyError:  # the reference indexes counts[j] of a level it never created (a miss)
+            want = False
+        assert orc.has_gram(q) == want, q
