@@ -502,6 +502,23 @@ def run_ours(args):
             msm = e0.elapsed_time(e1) / 20
             sweep[f"{args.mode}_B{Bs}"] = {"tokens_per_s": Bs * g / (msm * 1e-3), "ms_per_step": msm,
                                            "step_frac_of_hbm_peak": alg_bytes(Bs, g, V, dtype) / (msm * 1e-3) / 1e9 / peaks()[0]}
+            # the same step through GraphedVerify (captured once, device-resident Philox offset bumped inside the
+            # graph): one cudaGraphLaunch per step instead of four enqueues + Python argument handling
+            try:
+                gv = [sd.GraphedVerify(sets[j][0][:Bs], sets[j][1][:Bs], toks[j][:Bs], seed=1, **mode) for j in range(nbuf)]
+                for i in range(6):
+                    gv[i % nbuf]()
+                torch.cuda.synchronize()
+                e0.record()
+                for i in range(50):
+                    gv[i % nbuf]()
+                e1.record()
+                torch.cuda.synchronize()
+                msg = e0.elapsed_time(e1) / 50
+                sweep[f"{args.mode}_B{Bs}"]["graph_replay_ms_per_step"] = msg
+                del gv
+            except Exception as ex:
+                sweep[f"{args.mode}_B{Bs}"]["graph_replay_error"] = str(ex)[:120]
 
         # ---- the rest of BASELINE.json configs[1] (dtype / vocabulary / gamma axes) and the configs[2] shape
         # (B=64, gamma=4, nucleus p=0.9), each on its own inputs (two rotated sets; sets below the L2 size say so)

@@ -7,8 +7,13 @@
  * tree).  INTEGRATION.md shows the ctypes / torch.library binding a maintainer adds.
  *
  * Conventions: every function returns 0 on success, <0 for an invalid argument
- * (SPECDEC_ERR_*), >0 for a cudaError_t.  Nothing throws, nothing allocates (the caller
- * passes workspace), nothing synchronises: all work is enqueued on `stream`.  All pointers
+ * (SPECDEC_ERR_*), >0 for a cudaError_t.  Nothing throws, nothing synchronises: all work is enqueued on `stream`.
+ * Device memory is never allocated (the caller passes workspace; the n-gram tables are allocated by their create
+ * call).  ONE lazy host-side allocation exists: the first specdec_verify call of a device that takes the two-chunk
+ * pipeline (16-bit logits, B >= 128, plain modes) creates the library's auxiliary non-blocking stream and its
+ * fork/join events (cudaStreamCreateWithPriority + 9 cudaEventCreate, ~50 us, once per device, kept until exit).
+ * Thread safety: the entry points that enqueue work or change options serialise on one process-wide mutex for the
+ * duration of the enqueue; options (specdec_set_option) and profiling events are process-wide, not per call.  All pointers
  * are DEVICE pointers unless named host_*.  Strides are in ELEMENTS.  Logits are read-only
  * (unlike TopKProcessor._process, utils/logits_processor.py:62, which mutates its input).
  */

@@ -8,7 +8,7 @@ dispatch, no CPU fallback: ops raise if the library is missing or tensors are no
 """
 from . import _lib  # noqa: F401
 from . import ops  # noqa: F401  (registers torch.ops.specdec.*)
-from .ops import fused_verify, process_probs, sample_rows, sample_probs, philox_uniform, prune_kv, VerifyResult  # noqa: F401
+from .ops import fused_verify, process_probs, sample_rows, sample_probs, philox_uniform, prune_kv, VerifyResult, GraphedVerify, topk_ids, batch_writeback  # noqa: F401
 from .uniforms import PhiloxUniforms, InjectedUniforms, default_uniforms  # noqa: F401
 from .logits_processor import (LogitsProcessor, GreedyProcessor, MultinomialProcessor, TopKProcessor,  # noqa: F401
                                NucleusProcessor, TopKNucleusProcessor)

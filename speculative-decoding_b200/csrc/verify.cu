@@ -12,6 +12,7 @@
 // All arithmetic is the canonical fp32/integer arithmetic of canon.cuh, so results are bit-exact
 // against the CPU oracle for every launch geometry.
 #include <string.h>
+#include <mutex>
 #include "canon.cuh"
 #include "../../include/specdec_b200.h"
 
@@ -1499,6 +1500,11 @@ __global__ void philox_kernel(u64 seed, u64 offset, long long seq0, int B, int g
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
+// Process-wide state of the library: the tuning / test options below, the optional profiling events and the per-device
+// caches (function attributes, the auxiliary stream and its fork/join events).  Every entry point that launches work
+// or changes that state holds g_api_mu for the duration of its (host-side, microseconds) enqueue, so concurrent
+// calls from several host threads are serialised at the API boundary instead of racing on it.
+static std::mutex g_api_mu;
 static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};  // optional: start / after rowstats / after decide
 static int g_no_fast_ngram = 0;    // test hook: specdec_set_option("no_fast_ngram", 1)
 static int g_no_fast_nucleus = 0;  // test hook: specdec_set_option("no_fast_nucleus", 1)
@@ -2090,6 +2096,7 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
                    const int64_t* stop_tokens, int n_stop, int32_t* n_accepted, int64_t* next_token,
                    uint8_t* accept_mask, float* p_tok, float* q_tok, int32_t* first_stop, float* next_prob,
                    int32_t* packed, void* workspace, size_t workspace_bytes, specdec_stream_t stream) {
+  std::lock_guard<std::mutex> api_lock(g_api_mu);
   if (B < 0 || gamma < 0 || gamma > 64 || !target_logits) return SPECDEC_ERR_ARG;
   if (B == 0) return 0;
   const bool ngram = flags & SPECDEC_NGRAM;
@@ -2159,6 +2166,7 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
 }
 
 int specdec_set_option(const char* name, int value) {
+  std::lock_guard<std::mutex> api_lock(g_api_mu);
   if (!name) return SPECDEC_ERR_ARG;
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
@@ -2212,6 +2220,7 @@ int specdec_debug_timeline(const void* workspace, int B, int gamma, int V, unsig
 }
 
 int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {
+  std::lock_guard<std::mutex> api_lock(g_api_mu);
   g_ev[0] = (cudaEvent_t)ev_start; g_ev[1] = (cudaEvent_t)ev_mid; g_ev[2] = (cudaEvent_t)ev_end;
   return 0;
 }
@@ -2219,6 +2228,7 @@ int specdec_set_profile_events(void* ev_start, void* ev_mid, void* ev_end) {
 int specdec_process_probs(const void* logits, int dtype, int64_t rows, int V, int64_t stride, float temperature,
                           int top_k, float top_p, float* probs, float* row_stats, void* workspace,
                           size_t workspace_bytes, specdec_stream_t stream) {
+  std::lock_guard<std::mutex> api_lock(g_api_mu);
   if (rows < 0 || !logits) return SPECDEC_ERR_ARG;
   if (rows == 0) return 0;
   RowJob rj;
@@ -2241,6 +2251,7 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
                         int top_k, float top_p, int sample_mode, const float* u, uint64_t philox_seed,
                         uint64_t philox_offset, int64_t seq_id0, int lane_id, int64_t* tok, float* ptok,
                         void* workspace, size_t workspace_bytes, specdec_stream_t stream) {
+  std::lock_guard<std::mutex> api_lock(g_api_mu);
   if (rows < 0 || !logits || !tok) return SPECDEC_ERR_ARG;
   if (rows == 0) return 0;
   if (rows > 0x7fffffff) return SPECDEC_ERR_RANGE;

@@ -236,7 +236,11 @@ def prune_kv_op(tensors: List[Tensor], seq_lens: Tensor, discard: Tensor, zero_f
     """Per-sequence KV rollback on static [B,H,S_max,D] cache tensors (utils/caching.py:27-55 generalised).
     ptrs: optional cached device table of the tensors' addresses (int64 [n]); without zero_fill only the
     length vector changes and the tensors are not touched at all."""
-    _need_cuda(seq_lens, discard, *tensors)
+    _prune_kv_impl(tensors, seq_lens, discard, zero_fill, ptrs)
+
+
+def _prune_kv_impl(tensors, seq_lens: Tensor, discard: Tensor, zero_fill: bool, ptrs: Optional[Tensor]) -> None:
+    _need_cuda(seq_lens, discard, *(tensors if zero_fill else ()))
     if not tensors:
         return
     B, H, S, D = tensors[0].shape
@@ -344,6 +348,37 @@ def fused_verify(target_logits, draft_logits, draft_tokens, u_accept=None, u_sam
                                      L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
 
 
+class GraphedVerify:
+    """One verify step captured ONCE into a CUDA graph and replayed: the launch cost of a step drops from four
+    enqueues plus Python argument handling to a single cudaGraphLaunch, which is what bounds the step at small batch
+    (sampling/speculative_decoding.py is batch 1).  The inputs are static buffers (`target`, `draft`, `tokens`: pass
+    your model's output buffers to alias them, or copy into the ones allocated here); the Philox offset is a device
+    word the graph itself bumps, so every replay draws fresh uniforms (SPECDEC_OFFSET_DEVICE)."""
+
+    def __init__(self, target: Tensor, draft: Optional[Tensor], tokens: Tensor, *, seed=0, offset0=0, seq_id0=0,
+                 temperature=1.0, top_k=0, top_p=1.0, greedy=False, flags=0, stop_tokens=None):
+        _need_cuda(target, draft, tokens)
+        self.target, self.draft, self.tokens = target, draft, tokens
+        dev = target.device
+        self.offset = torch.full((1,), int(offset0), dtype=torch.int64, device=dev)
+        kw = dict(seed=seed, offset=self.offset, seq_id0=seq_id0, temperature=temperature, top_k=top_k, top_p=top_p,
+                  greedy=greedy, flags=flags, stop_tokens=stop_tokens)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):  # warm-up outside the capture: lazy per-device state, workspace growth
+            fused_verify(target, draft, tokens, None, None, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.result = fused_verify(target, draft, tokens, None, None, **kw)
+            self.offset.add_(1)
+
+    def __call__(self) -> VerifyResult:
+        """Replays the step on the buffers' CURRENT contents; the returned VerifyResult is overwritten by the next call."""
+        self.graph.replay()
+        return self.result
+
+
 def process_probs(logits, temperature=1.0, top_k=0, top_p=1.0):
     return process_probs_op(logits, float(temperature), int(top_k), float(top_p))
 
@@ -367,5 +402,7 @@ def philox_uniform(seed, offset, seq_id0, B, gamma, device="cuda"):
 def prune_kv(tensors, seq_lens, discard, zero_fill=False, ptrs=None):
     """zero_fill=False (default): only the length vector is updated -- the valid prefix [0, len_b) is the
     reference's pruned view; zero_fill=True also clears the discarded positions."""
-    prune_kv_op(list(tensors), seq_lens, discard, bool(zero_fill), ptrs)
+    # direct call of the implementation the registered op `specdec::prune_kv` runs (skips ~20 us of dispatcher
+    # overhead per call for a ~3 us kernel)
+    _prune_kv_impl(tensors, seq_lens, discard, bool(zero_fill), ptrs)
     return seq_lens

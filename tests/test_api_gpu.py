@@ -330,3 +330,21 @@ def test_verify_result_host_is_one_copy(oracle_mod):
                         stop_tokens=[int(case["draft_tokens"][0, 0])])
     n, x, fs = r.host()
     assert n == r.n_accepted.tolist() and x == r.next_token.tolist() and fs == r.first_stop.tolist()
+
+
+def test_graphed_verify_replays_match_eager_steps(oracle_mod):
+    import specdec_b200 as sd
+    case = make_case(B=3, gamma=4, V=32000, dtype="bf16", sigma=0.5, seed=13, oracle=oracle_mod, mode="topk50")
+    m = MODES["topk50"]
+    t, d, tk = case["target"].cuda(), case["draft"].cuda(), case["draft_tokens"].cuda()
+    gv = sd.GraphedVerify(t, d, tk, seed=21, offset0=5, **m)
+    for i in range(3):
+        r = gv()
+        e = sd.fused_verify(t, d, tk, None, None, seed=21, offset=5 + i, **m)
+        assert torch.equal(r.packed, e.packed) and torch.equal(r.first_stop, e.first_stop)
+    # the graph reads the buffers' current contents
+    t2 = torch.roll(t, 1, 0)
+    t.copy_(t2)
+    r = gv()
+    e = sd.fused_verify(t, d, tk, None, None, seed=21, offset=8, **m)
+    assert torch.equal(r.packed, e.packed)
