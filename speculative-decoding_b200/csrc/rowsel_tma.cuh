@@ -132,11 +132,12 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
   int stage = 0, par = 0;
   unsigned phase = 0;
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x, par ^= 1) {
-    // m1 >= m2 >= m3: the three largest STAGE maxima of my slice (k1, k2: the stages of the first two).  Every element
-    // outside stages k1 and k2 is <= m3, so after the row only those two stages (4 vectors each) have to be looked at
-    // again to list all my elements above a threshold th > m3.
-    float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, s = 0.0f;
-    int k1 = 0, k2 = 0;
+    // m1 >= m2 >= m3 >= m4: the four largest STAGE maxima of my slice (k1, k2, k3: the stages of the first three).
+    // Every element outside stages k1..k3 is <= m4, so after the row only those stages (4 vectors each) have to be
+    // looked at again to list all my elements above a threshold th > m4.  (With two tracked stages a third of the
+    // top-50 rows overflowed -- 50 candidates in 256 slices put three into one slice that often; with three it is 2 %.)
+    float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY, s = 0.0f;
+    int k1 = 0, k2 = 0, k3 = 0;
     for (int k = 0; k < nst; ++k) {
       mbar_wait(&full_bar[stage], phase);
       const unsigned off = (unsigned)k * RS2_STAGE_BYTES;
@@ -163,9 +164,11 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
           if (tid + q * RS2_CONSUMERS < nvec) accumulate16<DT>(a[q], c2, nmc2, acc);
         s = __fadd_rn(acc.x, acc.y);
       }
-      {  // branch-free insertion of vm into (m1, m2, m3)
-        const bool g1 = vm > m1, g2 = vm > m2;
-        m3 = g2 ? m2 : fmaxf(m3, vm);
+      {  // branch-free insertion of vm into (m1, m2, m3, m4)
+        const bool g1 = vm > m1, g2 = vm > m2, g3 = vm > m3;
+        m4 = g3 ? m3 : fmaxf(m4, vm);
+        k3 = g2 ? k2 : (g3 ? k : k3);
+        m3 = g2 ? m2 : (g3 ? vm : m3);
         k2 = g1 ? k1 : (g2 ? k : k2);
         m2 = g1 ? m1 : (g2 ? vm : m2);
         k1 = g1 ? k : k1;
@@ -245,14 +248,14 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
     float* cz = (float*)(rs2_dyn + (size_t)RS2_STAGES * RS2_STAGE_BYTES + par * RS2_CAND_BYTES);
     int* cj = (int*)(cz + RS2_CAP);
     if (ok && m1 >= th) {
-      // my slice holds candidates: look at stage k1 (and k2 if its maximum reaches th) again -- from L2, the row was
-      // streamed microseconds ago; a third hot stage is left to the fallback kernels
-      if (m3 >= th) s_ovf[par] = 1;
+      // my slice holds candidates: look at stage k1 (and k2, k3 if their maxima reach th) again -- from L2, the row
+      // was streamed microseconds ago; a fourth hot stage is left to the fallback kernels
+      if (m4 >= th) s_ovf[par] = 1;
       const char* row = (const char*)row_ptr<DT>(job, r);
-      const int nlook = (m2 >= th) ? 2 : 1;
+      const int nlook = (m3 >= th) ? 3 : ((m2 >= th) ? 2 : 1);
       constexpr int VPT = RS2_STAGE_BYTES / 16 / RS2_CONSUMERS;
       for (int which = 0; which < nlook; ++which) {
-        const int kk = which ? k2 : k1;
+        const int kk = which == 0 ? k1 : (which == 1 ? k2 : k3);
         uint4 a[VPT];
         int vv[VPT];
 #pragma unroll

@@ -1425,6 +1425,7 @@ __global__ void __launch_bounds__(NT, 1) decide_kernel(DecideJob job) {
 }
 
 #include "hybrid.cuh"
+#include "cluster_small.cuh"
 #include "rowsel_tma.cuh"
 
 // ---------------------------------------------------------------------------------------------
@@ -1645,8 +1646,9 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
 }
 
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+constexpr int CS_MAXCL = 16;  // largest cluster of the cluster-per-sequence path (cluster_small.cuh)
 struct WsLayout {
-  size_t rowout, zero, zero_bytes, zero_bytes_mega, tasks, status, samp, part, rpart, xs, dbg, klist, total;
+  size_t rowout, zero, zero_bytes, zero_bytes_mega, tasks, status, samp, part, rpart, xs, dbg, klist, cpart, total;
   int nseg_pad, xs_stride;
 };
 static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
@@ -1670,6 +1672,7 @@ static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   w.samp = o; o = al256(o + (size_t)B * 4 * SAMP_N);
   w.dbg = o; o = al256(o + (size_t)(16 + B * 8 + 1024) * 8);          // megakernel: debug timeline + SM of every CTA
   w.klist = o; o = al256(o + (size_t)R * KL_MAX * sizeof(int2));      // masked modes: kept-token lists of small kept sets
+  w.cpart = o; o = al256(o + (size_t)R * CS_MAXCL * sizeof(float2));  // cluster-per-sequence path: (max, sum) of every row slice
   w.total = o;
   return w;
 }
@@ -1981,11 +1984,64 @@ static cudaError_t launch_mega(const DecideJob& dj, HybridWs ws, const MegaCfg& 
   return cudaLaunchKernelEx(&lc, kern, dj, ws, cfg);
 }
 
+// Small batches of the plain modes: one launch, one thread-block cluster per sequence (cluster_small.cuh).
+// Returns false when the shape is not eligible or the device cannot host one cluster (the caller takes the pipeline).
+static int g_small_b = 64;      // largest batch that takes the cluster path (option "small_b"; 0 = never)
+static int g_small_cl = 16;     // CTAs per cluster (option "small_cl": 8 or 16)
+template <int DT>
+static bool launch_cluster_small(const DecideJob& dj, HybridWs ws, const WsLayout& wl, void* workspace, int B, cudaStream_t st,
+                                 cudaError_t& err) {
+  const RowJob& rj = dj.rj;
+  if (B > g_small_b || dj.gamma <= 0 || rj.top_k > 0 || rj.use_p || (dj.flags & SPECDEC_NGRAM) || g_no_fused_tail) return false;
+  const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5);
+  int CL = g_small_cl >= 16 ? 16 : 8;
+  if (nseg < CL) return false;  // tiny vocabularies: nothing to split
+  auto kern = dj.greedy ? verify_cluster_kernel<DT, true> : verify_cluster_kernel<DT, false>;
+  static int ok_dev[MAXDEV][2][2];  // per device / greedy / (CL == 16): 0 unknown, 1 usable, -1 not usable
+  static size_t smem_dev[MAXDEV][2][2];
+  const int dv = cur_dev(), gi = dj.greedy ? 1 : 0;
+  for (; CL >= 8; CL >>= 1) {
+    const int ci = CL == 16 ? 1 : 0;
+    const int spc = (nseg + CL - 1) / CL;
+    const size_t smem = (size_t)spc * TF_SEG_BYTES;
+    if (smem > 200 * 1024) return false;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cudaLaunchConfig_t lc;
+    memset(&lc, 0, sizeof(lc));
+    lc.stream = st; lc.attrs = at; lc.numAttrs = 1;
+    lc.gridDim = dim3((unsigned)B * CL); lc.blockDim = dim3(CS_T); lc.dynamicSmemBytes = smem;
+    if (ok_dev[dv][gi][ci] == 0 || smem_dev[dv][gi][ci] != smem) {
+      int ok = 1, ncl = 0;
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) ok = -1;
+      if (ok == 1 && CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = -1;
+      if (ok == 1 && (cudaOccupancyMaxActiveClusters(&ncl, kern, &lc) != cudaSuccess || ncl < 1)) ok = -1;
+      cudaGetLastError();  // (a failed query must not poison the caller's next launch check)
+      ok_dev[dv][gi][ci] = ok; smem_dev[dv][gi][ci] = smem;
+    }
+    if (ok_dev[dv][gi][ci] != 1) continue;
+    ws.fused = 1;
+    if ((err = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st)) != cudaSuccess) return true;
+    if (g_ev[0]) cudaEventRecord(g_ev[0], st);
+    err = cudaLaunchKernelEx(&lc, kern, dj, ws, (float2*)((char*)workspace + wl.cpart), spc, CL);
+    if (g_ev[1]) cudaEventRecord(g_ev[1], st);
+    if (g_ev[2]) cudaEventRecord(g_ev[2], st);
+    if (err == cudaSuccess) err = cudaGetLastError();
+    return true;
+  }
+  return false;
+}
+
 template <int DT>
 static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* workspace, int B, cudaStream_t st) {
   const RowJob& rj = dj.rj;
   const bool masked = rj.top_k > 0 || rj.use_p;
   HybridWs ws = ws_pointers(wl, workspace, B, rj.R);
+  {
+    cudaError_t ce = cudaSuccess;
+    if (launch_cluster_small<DT>(dj, ws, wl, workspace, B, st, ce)) return ce;
+  }
   MegaCfg mcfg;
   int mgrid = 0;
   const bool mega = mega_config<DT>(dj, B, mcfg, mgrid);
@@ -2171,7 +2227,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_small_b = 64; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2188,6 +2244,8 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "mega_dbg")) { g_mega_dbg = value; return 0; }
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   if (!strcmp(name, "no_klist")) { g_no_klist = value; return 0; }
+  if (!strcmp(name, "small_b")) { g_small_b = value; return 0; }
+  if (!strcmp(name, "small_cl")) { g_small_cl = value; return 0; }
   if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
   if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }
   if (!strcmp(name, "no_hist_nucleus")) { g_no_hist_nucleus = value; return 0; }

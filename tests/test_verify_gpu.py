@@ -23,6 +23,19 @@ def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
     r = sd.fused_verify(tgt.to(dev), None if ngram else case["draft"].to(dev), case["draft_tokens"].to(dev),
                         case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
     torch.cuda.synchronize()
+    if tgt.shape[0] <= 64:
+        # small batches of the plain modes take the one-launch cluster path (csrc/cluster_small.cuh) by default: every
+        # case is ALSO run through the three-launch pipeline and through 8-CTA clusters; the decisions must be identical
+        lib = sd._lib.lib()
+        for opt, val in ((b"small_b", 0), (b"small_cl", 8)):
+            assert lib.specdec_set_option(opt, val) == 0
+            r2 = sd.fused_verify(tgt.to(dev), None if ngram else case["draft"].to(dev), case["draft_tokens"].to(dev),
+                                 case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
+            torch.cuda.synchronize()
+            assert lib.specdec_set_option(b"small_b", 64) == 0 and lib.specdec_set_option(b"small_cl", 16) == 0
+            for a in ("n_accepted", "next_token", "accept_mask", "first_stop", "packed"):
+                assert torch.equal(getattr(r, a), getattr(r2, a)), (a, opt)
+            np.testing.assert_allclose(r2.p_tok.cpu().numpy(), r.p_tok.cpu().numpy(), rtol=1e-5, atol=0)
     return o, r
 
 
