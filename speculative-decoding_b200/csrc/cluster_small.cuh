@@ -10,8 +10,9 @@
 //      phase is latency bound), online (max, sum of MUFU ex2), partials to the workspace;        barrier.cluster
 //   2. warp 0 of CTA 0 merges the partials into the RowOut records and runs plan_sequence (accept tests with the
 //      1e-3 margin, hybrid.cuh) -- the same code the pipeline's plan_kernel runs;                  barrier.cluster
-//   3. every CTA runs tail_item (tail_fused.cuh) on its slice of the deciding row pair: canonical weights cached in
-//      shared memory, exact normalisers, residual partial sums, token location.
+//   3. every CTA runs mega_item (mega.cuh: tail_item with the exchange through self-validating words) on its slice of
+//      the deciding row pair: canonical weights cached in shared memory, exact normalisers, residual partial sums,
+//      token location.
 // Same integers as the pipeline => bit-identical results.  Exchanges go through the (L2-resident) workspace with
 // release/acquire cluster barriers; nothing spins except tail_item's own bounded group waits.
 #pragma once
@@ -86,15 +87,30 @@ __global__ void __launch_bounds__(CS_T) verify_cluster_kernel(DecideJob job, Hyb
         }
       }
     }
+    // per-warp (max, sum) of every row of the group -> shared memory; one barrier for the whole group
+    float* wm = reinterpret_cast<float*>(ecache);  // [CS_T / 32][CS_RG][2] floats of the (still unused) weight cache
 #pragma unroll
     for (int q = 0; q < CS_RG; ++q) {
-      if (k0 + q < rps) {  // block-uniform
-        const float M = block_max_f(m[q], sh.shf);
-        const float sv = (m[q] > -INFINITY) ? __fmul_rn(s[q], ex2_approx(__fmul_rn(__fsub_rn(m[q], M), c))) : 0.0f;
-        const float S = block_sum_f(sv, sh.shf);
-        if (tid == 0) cpart[((size_t)b * rps + k0 + q) * CL + ch] = make_float2(M, S);
-      }
+      const float M = warp_max_f(m[q]);
+      float sv = (m[q] > -INFINITY) ? __fmul_rn(s[q], ex2_approx(__fmul_rn(__fsub_rn(m[q], M), c))) : 0.0f;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sv += __shfl_xor_sync(0xffffffffu, sv, o);
+      if (lane == 0) { wm[((tid >> 5) * CS_RG + q) * 2] = M; wm[((tid >> 5) * CS_RG + q) * 2 + 1] = sv; }
     }
+    __syncthreads();
+    if (tid < CS_RG && k0 + tid < rps) {
+      float M = -INFINITY;
+#pragma unroll
+      for (int w = 0; w < CS_T / 32; ++w) M = fmaxf(M, wm[(w * CS_RG + tid) * 2]);
+      float S = 0.0f;
+#pragma unroll
+      for (int w = 0; w < CS_T / 32; ++w) {
+        const float mw = wm[(w * CS_RG + tid) * 2];
+        if (mw > -INFINITY) S = __fadd_rn(S, __fmul_rn(wm[(w * CS_RG + tid) * 2 + 1], ex2_approx(__fmul_rn(__fsub_rn(mw, M), c))));
+      }
+      cpart[((size_t)b * rps + k0 + tid) * CL + ch] = make_float2(M, S);
+    }
+    __syncthreads();
   }
   cluster_sync_all();
   // ---- 2. merge + plan: one warp of the cluster
@@ -121,6 +137,7 @@ __global__ void __launch_bounds__(CS_T) verify_cluster_kernel(DecideJob job, Hyb
   }
   cluster_sync_all();
   // ---- 3. everything after the plan, slice ch of CL
-  const int seq_tasks = __ldcg(&ws.seq_tasks[b]);
-  tail_item<DT, GREEDY>(job, ws, b, ch, CL, segs_per_cta, ecache, sh, seq_tasks, false, make_int4(0, 0, 0, 0), 0);
+  __shared__ volatile int credit;
+  const int4 rec = __ldcg((const int4*)(ws.samp + b * SAMP_N)), rec2 = __ldcg((const int4*)(ws.samp + b * SAMP_N) + 1);
+  mega_item<DT, GREEDY, 4>(job, ws, b, ch, CL, segs_per_cta, ecache, sh, rec2.y, rec, rec2.x, &credit);
 }

@@ -357,7 +357,7 @@ __device__ __forceinline__ bool slots_collect(const HybridWs& ws, int b, int S, 
   return true;
 }
 
-template <int DT, bool GREEDY>
+template <int DT, bool GREEDY, int NS_ITEM = MG_NS>
 __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& ws, const int b, const int ch, const int S,
                                           const int segs_per_cta, float4* ecache, TailSh& sh, const int seq_tasks, int4 rec,
                                           int mcq_bits, volatile int* credit) {
@@ -429,7 +429,7 @@ __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& 
     const bool qal = (((size_t)qrowp) & 15) == 0;
     // ---- phase A: canonical weights of my slice -> shared memory; partial normalisers -> my slot ----
     u64 sp = 0, sq = 0;
-    pair_sums<DT, true, MG_NS>(prowp, qrowp, pal, qal, V, c, mcp, mcq, s0, s1, ecache, sp, sq);
+    pair_sums<DT, true, NS_ITEM>(prowp, qrowp, pal, qal, V, c, mcp, mcq, s0, s1, ecache, sp, sq);
     block_sum2_u64(sp, sq, sh.sh64);
     if (tid == 0) {
       dbg_stamp_max(ws, 16 + b * 8 + 7);
@@ -533,6 +533,29 @@ __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& 
   mega_finalize<DT>(job, ws, b, &sh);
   if (tid == 0) dbg_stamp_max(ws, 16 + b * 8 + 6);
   return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tail_slots_kernel: the fused tail of the three-launch pipeline (tail_fused_kernel's role and launch geometry) with
+// mega_item's exchange.  A tail CTA's life is a chain of dependent L2 round trips, not arithmetic (~2 us of issue
+// in a ~13 us life at 4 CTAs / SM: profiles/README.md): ticket, plan record, row loads, {2 atomics, fence, counter
+// atomic, poll, 2 loads} for the normalisers, {atomic, fence, counter atomic with return} for the hand-over to the
+// finalizer.  Self-validating words cut the two exchanges to {2 stores | poll} and {stores}: no fence, no atomic
+// whose return value is waited for, 19 of 20 CTAs leave right after their last store.
+// ---------------------------------------------------------------------------------------------
+template <int DT, bool GREEDY>
+__global__ void __launch_bounds__(TF_T, 4) tail_slots_kernel(DecideJob job, HybridWs ws, int segs_per_cta, int TF_CH) {
+  extern __shared__ __align__(16) float4 ecache[];
+  __shared__ TailSh sh;
+  __shared__ int sh_ticket;
+  __shared__ volatile int credit;
+  if (threadIdx.x == 0) sh_ticket = atomicAdd(ws.ticket, 1);  // (taken before the dependency wait, see tail_fused_kernel)
+  grid_dependency_wait();
+  __syncthreads();
+  const int b = sh_ticket / TF_CH, ch = sh_ticket - b * TF_CH;
+  // the sequence's whole plan record in one round trip: {n, mode, p-row position, mc_p | mc_q, exact tasks, -, -}
+  const int4 rec = __ldcg((const int4*)(ws.samp + b * SAMP_N)), rec2 = __ldcg((const int4*)(ws.samp + b * SAMP_N) + 1);
+  mega_item<DT, GREEDY, 4>(job, ws, b, ch, TF_CH, segs_per_cta, ecache, sh, rec2.y, rec, rec2.x, &credit);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1524,6 +1524,7 @@ static bool pdl_enabled(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
 }
+static int g_tail_slots = 1;     // fused tail: inter-CTA exchange through self-validating words (0: atomics + counters)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 static int g_no_klist = 0;       // test hook: specdec_set_option("no_klist", 1) => masked modes always draw by a sweep over the row
 // per-device caches (function attributes are per device; one process may drive several GPUs)
@@ -1656,6 +1657,7 @@ static WsLayout ws_layout(long long B, int gamma, int V, long long R) {
   const int NV = (V + 7) >> 3;
   w.nseg_pad = ((NV + 31) >> 5) + 1;
   w.xs_stride = (w.nseg_pad - 1 + MG_MIN_SPC - 1) / MG_MIN_SPC;  // exact items per sequence at the smallest item size
+  if (w.xs_stride < 64) w.xs_stride = 64;                         // (tail_slots_kernel: up to 64 slices per sequence)
   size_t o = 0;
   w.rowout = o; o = al256(o + (size_t)R * sizeof(RowOut));
   w.zero = o;  // ---- zeroed at the head of every call
@@ -1837,15 +1839,18 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5), spc = (nseg + nch - 1) / nch;
   const size_t tf_smem = (size_t)spc * TF_SEG_BYTES;
   bool fused_ok = !masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail;
-  auto tail = dj.greedy ? tail_fused_kernel<DT, true> : tail_fused_kernel<DT, false>;
+  // exchange between the CTAs of a sequence: self-validating words (tail_slots_kernel, default) or atomics + counters
+  const bool slots = g_tail_slots && nch <= ws.xs_stride;
+  auto tail = slots ? (dj.greedy ? tail_slots_kernel<DT, true> : tail_slots_kernel<DT, false>)
+                    : (dj.greedy ? tail_fused_kernel<DT, true> : tail_fused_kernel<DT, false>);
   if (fused_ok) {
     // The nch CTAs of a sequence wait for one another (tail_fused.cuh): that needs at least nch CTAs co-resident on
     // the device (ticket order then guarantees progress).  Under an SM limit (MPS / green contexts) or with a huge
     // slice the occupancy query says otherwise and the step takes the split pipeline, whose CTAs never wait.
-    static size_t attr_smem_dev[MAXDEV][2];  // dynamic shared memory already granted (per device, per instantiation)
-    static size_t occ_smem_dev[MAXDEV][2];
-    static int occ_dev[MAXDEV][2];
-    const int dv = cur_dev(), gi = dj.greedy ? 1 : 0;
+    static size_t attr_smem_dev[MAXDEV][4];  // dynamic shared memory already granted (per device, per instantiation)
+    static size_t occ_smem_dev[MAXDEV][4];
+    static int occ_dev[MAXDEV][4];
+    const int dv = cur_dev(), gi = (dj.greedy ? 1 : 0) + (slots ? 2 : 0);
     if (attr_smem_dev[dv][gi] < tf_smem) {
       cudaError_t e = cudaFuncSetAttribute(tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tf_smem);
       if (e != cudaSuccess) return e;
@@ -1930,6 +1935,7 @@ static void sub_job(const DecideJob& dj, const HybridWs& ws, int b0, int nb, int
   w.rows_done = ws.rows_done + b0; w.seq_tasks = ws.seq_tasks + b0;
   w.exact_done = ws.exact_done + b0; w.part_done = ws.part_done + b0;
   w.part = ws.part + (size_t)b0 * ws.nseg_pad;
+  w.xs = ws.xs + (size_t)b0 * ws.xs_stride * 4;
 }
 
 // The plain modes on TMA-eligible 16-bit rows: one persistent cooperative launch (mega.cuh).  mega_config() returns
@@ -1999,6 +2005,7 @@ static bool launch_cluster_small(const DecideJob& dj, HybridWs ws, const WsLayou
   auto kern = dj.greedy ? verify_cluster_kernel<DT, true> : verify_cluster_kernel<DT, false>;
   static int ok_dev[MAXDEV][2][2];  // per device / greedy / (CL == 16): 0 unknown, 1 usable, -1 not usable
   static size_t smem_dev[MAXDEV][2][2];
+  static size_t attr_dev[MAXDEV][2];  // dynamic shared memory granted to the kernel so far (only ever raised)
   const int dv = cur_dev(), gi = dj.greedy ? 1 : 0;
   for (; CL >= 8; CL >>= 1) {
     const int ci = CL == 16 ? 1 : 0;
@@ -2014,7 +2021,10 @@ static bool launch_cluster_small(const DecideJob& dj, HybridWs ws, const WsLayou
     lc.gridDim = dim3((unsigned)B * CL); lc.blockDim = dim3(CS_T); lc.dynamicSmemBytes = smem;
     if (ok_dev[dv][gi][ci] == 0 || smem_dev[dv][gi][ci] != smem) {
       int ok = 1, ncl = 0;
-      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) ok = -1;
+      if (attr_dev[dv][gi] < smem) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) ok = -1;
+        else attr_dev[dv][gi] = smem;
+      }
       if (ok == 1 && CL > 8 && cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) ok = -1;
       if (ok == 1 && (cudaOccupancyMaxActiveClusters(&ncl, kern, &lc) != cudaSuccess || ncl < 1)) ok = -1;
       cudaGetLastError();  // (a failed query must not poison the caller's next launch check)
@@ -2022,7 +2032,7 @@ static bool launch_cluster_small(const DecideJob& dj, HybridWs ws, const WsLayou
     }
     if (ok_dev[dv][gi][ci] != 1) continue;
     ws.fused = 1;
-    if ((err = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes, st)) != cudaSuccess) return true;
+    if ((err = cudaMemsetAsync((char*)workspace + wl.zero, 0, wl.zero_bytes_mega, st)) != cudaSuccess) return true;
     if (g_ev[0]) cudaEventRecord(g_ev[0], st);
     err = cudaLaunchKernelEx(&lc, kern, dj, ws, (float2*)((char*)workspace + wl.cpart), spc, CL);
     if (g_ev[1]) cudaEventRecord(g_ev[1], st);
@@ -2045,7 +2055,9 @@ static cudaError_t launch_hybrid(DecideJob& dj, const WsLayout& wl, void* worksp
   MegaCfg mcfg;
   int mgrid = 0;
   const bool mega = mega_config<DT>(dj, B, mcfg, mgrid);
-  cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, mega ? wl.zero_bytes_mega : wl.zero_bytes, st);
+  // (the self-validating exchange words of tail_slots_kernel / the megakernel live in the larger zeroed region)
+  const bool slots_zero = !masked && dj.gamma > 0 && g_tail_slots && !g_no_fused_tail;
+  cudaError_t e = cudaMemsetAsync((char*)workspace + wl.zero, 0, (mega || slots_zero) ? wl.zero_bytes_mega : wl.zero_bytes, st);
   if (e != cudaSuccess) return e;
   if (mega) {
     if (g_mega_dbg) {  // timeline: minima start at ~0ull, maxima at 0
@@ -2227,7 +2239,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_small_b = 64; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_tail_slots = 1; g_small_b = 64; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2245,6 +2257,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "no_fast_nucleus")) { g_no_fast_nucleus = value; return 0; }
   if (!strcmp(name, "no_klist")) { g_no_klist = value; return 0; }
   if (!strcmp(name, "small_b")) { g_small_b = value; return 0; }
+  if (!strcmp(name, "tail_slots")) { g_tail_slots = value; return 0; }
   if (!strcmp(name, "small_cl")) { g_small_cl = value; return 0; }
   if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
   if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }

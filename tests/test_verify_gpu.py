@@ -27,12 +27,15 @@ def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
         # small batches of the plain modes take the one-launch cluster path (csrc/cluster_small.cuh) by default: every
         # case is ALSO run through the three-launch pipeline and through 8-CTA clusters; the decisions must be identical
         lib = sd._lib.lib()
-        for opt, val in ((b"small_b", 0), (b"small_cl", 8)):
-            assert lib.specdec_set_option(opt, val) == 0
+        for opts in ({b"small_b": 0}, {b"small_cl": 8}, {b"small_b": 0, b"tail_slots": 0}):
+            opt = tuple(opts.items())
+            for k_, v_ in opts.items():
+                assert lib.specdec_set_option(k_, v_) == 0
             r2 = sd.fused_verify(tgt.to(dev), None if ngram else case["draft"].to(dev), case["draft_tokens"].to(dev),
                                  case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
             torch.cuda.synchronize()
             assert lib.specdec_set_option(b"small_b", 64) == 0 and lib.specdec_set_option(b"small_cl", 16) == 0
+            assert lib.specdec_set_option(b"tail_slots", 1) == 0
             for a in ("n_accepted", "next_token", "accept_mask", "first_stop", "packed"):
                 assert torch.equal(getattr(r, a), getattr(r2, a)), (a, opt)
             np.testing.assert_allclose(r2.p_tok.cpu().numpy(), r.p_tok.cpu().numpy(), rtol=1e-5, atol=0)
@@ -448,8 +451,17 @@ def test_fused_tail_equals_split_kernels_incl_ambiguous_accept_tests(oracle_mod,
     kw = dict(greedy=greedy)
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], ua, case["u_sample"], **kw)
     args = [case[k].cuda() for k in ("target", "draft", "draft_tokens", "u_accept", "u_sample")]
+    # (the fused and the split tails of the three-launch pipeline: same row kernel, so the fast p/q values of the
+    # sure positions coincide bit for bit; the one-launch cluster path of small batches sums them in another order)
+    assert lib.specdec_set_option(b"small_b", 0) == 0
     r1 = sd.fused_verify(*args, **kw)
     torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"tail_slots", 0) == 0
+    r1b = sd.fused_verify(*args, **kw)   # atomics + counters exchange (tail_fused_kernel)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"tail_slots", 1) == 0
+    for a in ("n_accepted", "next_token", "accept_mask", "packed", "next_prob", "p_tok", "q_tok", "first_stop"):
+        assert torch.equal(getattr(r1, a), getattr(r1b, a)), a
     assert lib.specdec_set_option(b"no_fused_tail", 1) == 0
     try:
         r2 = sd.fused_verify(*args, **kw)
