@@ -13,6 +13,11 @@
 //   3. every CTA runs mega_item (mega.cuh: tail_item with the exchange through self-validating words) on its slice of
 //      the deciding row pair: canonical weights cached in shared memory, exact normalisers, residual partial sums,
 //      token location.
+// MEASURED (B200, graph-replayed step, bf16, gamma 4, V 128256): 36 / 68 / 121 us at B = 1 / 32 / 64 against 34 / 47 / 67 us
+// for the three-launch pipeline -- the phases of one sequence run back to back here (statistics, plan by ONE warp
+// while 127 wait, exact item), where the pipeline overlaps them across sequences.  The path is therefore OPT-IN
+// (specdec_set_option("small_b", B_max)); it stays built and parity-tested because it is the only path whose
+// inter-CTA waits are co-scheduled by hardware (no ticket-order argument), e.g. under MPS SM limits.
 // Same integers as the pipeline => bit-identical results.  Exchanges go through the (L2-resident) workspace with
 // release/acquire cluster barriers; nothing spins except tail_item's own bounded group waits.
 #pragma once

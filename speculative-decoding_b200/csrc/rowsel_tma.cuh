@@ -11,7 +11,7 @@
 //                   top-p: the largest value whose slice maxima alone out-weigh top_p * S1 -- then every thread whose
 //                   maximum reaches the threshold looks at its one or two hot STAGES again (4 vectors each, from L2: 2
 //                   CTAs per SM keep 76 MB of rows in flight) and appends its elements above it to a candidate buffer
-//   2 selector warps  exact selection among the candidates (select_cut_group, integer arithmetic), RowOut record and
+//   selector warp   exact selection among the candidates (select_cut_group, integer arithmetic), RowOut record and
 //                   kept-token list -- concurrently with the consumers streaming the next row (two candidate buffers)
 // Rows it cannot resolve (candidate overflow, ambiguous top-p bracket, flat top-p rows) stay unflagged and are redone
 // by nucleus_hist_kernel / rowstats_kernel.  Results are bit-identical to those kernels: the same selection code runs
@@ -19,7 +19,8 @@
 #pragma once
 
 constexpr int RS2_CONSUMERS = 256;
-constexpr int RS2_THREADS = RS2_CONSUMERS + 96;  // + producer warp + two selector warps (one per candidate buffer)
+constexpr int RS2_SELECTORS = 1;  // selector warps (2: one per candidate buffer -- measured slower: 352 vs 310 us on top-k + top-p)
+constexpr int RS2_THREADS = RS2_CONSUMERS + 32 + 32 * RS2_SELECTORS;  // + producer warp + selector warp(s)
 constexpr int RS2_STAGES = 4;
 constexpr int RS2_STAGE_BYTES = 16384;
 constexpr int RS2_CAP = 1024;  // candidates per buffer (== WARP_SELECT_MAX: one warp selects)
@@ -76,8 +77,9 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
   if (warp >= RS2_CONSUMERS / 32 + 1) {
     // ---------------- selector warps: warp s owns candidate buffer s, i.e. every second row of this CTA (the exact
     // selection of a top-k + top-p row takes one warp longer than the consumers need to stream a row)
-    const int par = warp - (RS2_CONSUMERS / 32 + 1);
-    for (long long r = blockIdx.x + (long long)par * gridDim.x; r < job.R; r += 2ll * gridDim.x) {
+    int par = warp - (RS2_CONSUMERS / 32 + 1);
+    for (long long r = blockIdx.x + (long long)par * gridDim.x; r < job.R; r += (long long)RS2_SELECTORS * gridDim.x,
+                   par = (RS2_SELECTORS == 1) ? (par ^ 1) : par) {
       if (lane == 0)
         while (buf_state[par] != 1) __nanosleep(64);
       __syncwarp();

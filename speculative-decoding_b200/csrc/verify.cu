@@ -1992,7 +1992,10 @@ static cudaError_t launch_mega(const DecideJob& dj, HybridWs ws, const MegaCfg& 
 
 // Small batches of the plain modes: one launch, one thread-block cluster per sequence (cluster_small.cuh).
 // Returns false when the shape is not eligible or the device cannot host one cluster (the caller takes the pipeline).
-static int g_small_b = 64;      // largest batch that takes the cluster path (option "small_b"; 0 = never)
+static int g_small_b = 0;       // largest batch that takes the cluster path (option "small_b"; 0 = never, the default:
+                                // measured on B200 the one-launch path LOSES to the pipeline -- graph-replayed step
+                                // 36 / 68 / 121 us vs 34 / 47 / 67 us at B = 1 / 32 / 64 -- its three phases serialise
+                                // per sequence what the pipeline overlaps across sequences; kept opt-in and tested)
 static int g_small_cl = 16;     // CTAs per cluster (option "small_cl": 8 or 16)
 template <int DT>
 static bool launch_cluster_small(const DecideJob& dj, HybridWs ws, const WsLayout& wl, void* workspace, int B, cudaStream_t st,
@@ -2239,7 +2242,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_tail_slots = 1; g_small_b = 64; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_tail_slots = 1; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }

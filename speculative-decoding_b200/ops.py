@@ -46,8 +46,19 @@ def _rows_view(logits: Tensor) -> Tuple[Tensor, int, int, int]:
 _WS_CACHE = {}
 
 
-def _workspace(dev, nbytes: int) -> Tensor:
-    """Per-device scratch, grown on demand and reused across calls (all use is stream-ordered)."""
+_WS_BYTES = {}
+
+
+def _workspace(dev, B_or_bytes: int, gamma: int = -1, V: int = 0, lib=None) -> Tensor:
+    """Per-device-and-stream scratch, grown on demand and reused across calls (all use is stream-ordered).
+    Called with (dev, nbytes) or, for verify, with (dev, B, gamma, V, lib): the size query is cached per shape."""
+    if gamma >= 0:
+        k = (B_or_bytes, gamma, V)
+        nbytes = _WS_BYTES.get(k)
+        if nbytes is None:
+            nbytes = _WS_BYTES[k] = lib.specdec_verify_workspace_bytes(B_or_bytes, gamma, V)
+    else:
+        nbytes = B_or_bytes
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WS_CACHE.get(key)
     if ws is None or ws.numel() < nbytes:
@@ -90,24 +101,20 @@ def _verify_impl(target_logits: Tensor, draft_logits: Optional[Tensor], draft_to
         n_stop = stop_tokens.numel()
     # one allocation for all outputs: [n_acc i32 | first_stop i32 | next_prob f32 | p_tok f32 | q_tok f32 |
     #                                  packed i32 | next_token i64 (8-aligned) | mask u8]
+    # Only addresses are computed here; the tensor views are created lazily by VerifyResult (a dozen view objects
+    # cost more host time than the whole enqueue at small batch).
     g = gamma
-    n32 = 3 * B + 2 * B * g + B * (g + 2)
-    n32 += n32 & 1
+    n32 = _n32(B, g)
     buf = torch.empty(n32 * 4 + B * 8 + B * g, dtype=torch.uint8, device=dev)
-    i32 = buf[:n32 * 4].view(torch.int32)
-    f32 = buf[:n32 * 4].view(torch.float32)
-    n_acc, fstop, nprob = i32[0:B], i32[B:2 * B], f32[2 * B:3 * B]
-    o = 3 * B
-    p_tok = f32[o:o + B * g].view(B, g); o += B * g
-    q_tok = f32[o:o + B * g].view(B, g); o += B * g
-    packed = i32[o:o + B * (g + 2)].view(B, g + 2)
-    nxt = buf[n32 * 4:n32 * 4 + B * 8].view(torch.int64)
-    mask = buf[n32 * 4 + B * 8:].view(B, g)
-    lib = L.lib()
-    ws_bytes = lib.specdec_verify_workspace_bytes(B, gamma, V)
-    ws = _workspace(dev, ws_bytes)
-    sd = draft_logits.stride() if draft_logits is not None else (0, 0, 1)
     base = buf.data_ptr()
+    o_pt = base + 12 * B
+    o_qt = o_pt + 4 * B * g
+    o_pk = o_qt + 4 * B * g
+    o_nx = base + n32 * 4
+    o_mk = o_nx + 8 * B
+    lib = L.lib()
+    ws = _workspace(dev, B, gamma, V, lib)
+    sd = draft_logits.stride() if draft_logits is not None else (0, 0, 1)
     if torch.cuda.current_device() != dev.index:
         torch.cuda.set_device(dev)
     rc = lib.specdec_verify(
@@ -115,11 +122,29 @@ def _verify_impl(target_logits: Tensor, draft_logits: Optional[Tensor], draft_to
         seed & 0xFFFFFFFFFFFFFFFF, offset & 0xFFFFFFFFFFFFFFFF, seq_id0, B, gamma, V,
         target_logits.stride(0), target_logits.stride(1), sd[0], sd[1],
         float(temperature), int(top_k), float(top_p), int(sample_mode), int(flags),
-        _ptr(stop_tokens), n_stop, n_acc.data_ptr(), nxt.data_ptr(), mask.data_ptr() if g else None,
-        p_tok.data_ptr() if g else None, q_tok.data_ptr() if g else None, fstop.data_ptr(),
-        nprob.data_ptr(), packed.data_ptr(), ws.data_ptr(), ws.numel(), _stream())
+        _ptr(stop_tokens), n_stop, base, o_nx, o_mk if g else None,
+        o_pt if g else None, o_qt if g else None, base + 4 * B,
+        base + 8 * B, o_pk, ws.data_ptr(), ws.numel(), _stream())
     L.check(rc, "specdec_verify")
-    return [n_acc, nxt, mask, p_tok, q_tok, fstop, nprob, packed, buf]
+    return buf, B, g
+
+
+def _n32(B: int, g: int) -> int:
+    n32 = 3 * B + 2 * B * g + B * (g + 2)
+    return n32 + (n32 & 1)
+
+
+def _verify_views(buf: Tensor, B: int, g: int) -> List[Tensor]:
+    n32 = _n32(B, g)
+    i32 = buf[:n32 * 4].view(torch.int32)
+    f32 = buf[:n32 * 4].view(torch.float32)
+    o = 3 * B
+    p_tok = f32[o:o + B * g].view(B, g); o += B * g
+    q_tok = f32[o:o + B * g].view(B, g); o += B * g
+    packed = i32[o:o + B * (g + 2)].view(B, g + 2)
+    nxt = buf[n32 * 4:n32 * 4 + B * 8].view(torch.int64)
+    mask = buf[n32 * 4 + B * 8:].view(B, g)
+    return [i32[0:B], nxt, mask, p_tok, q_tok, i32[B:2 * B], f32[2 * B:3 * B], packed]
 
 
 @torch.library.custom_op("specdec::verify", mutates_args=())
@@ -128,8 +153,9 @@ def verify_op(target_logits: Tensor, draft_logits: Optional[Tensor], draft_token
               temperature: float, top_k: int, top_p: float, sample_mode: int, flags: int,
               stop_tokens: Optional[Tensor]) -> List[Tensor]:
     # custom ops may not return views of one buffer: clone the (tiny) outputs
-    return [t.clone() for t in _verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, seed, offset,
-                                            seq_id0, temperature, top_k, top_p, sample_mode, flags, stop_tokens)[:8]]
+    return [t.clone() for t in _verify_views(*_verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, seed,
+                                                           offset, seq_id0, temperature, top_k, top_p, sample_mode, flags,
+                                                           stop_tokens))]
 
 
 @verify_op.register_fake
@@ -301,24 +327,34 @@ def batch_writeback(res, generated: Tensor, step, g: int, finished: Tensor, n_ac
 
 # ---- convenient python wrappers -------------------------------------------------------------
 class VerifyResult:
-    __slots__ = ("n_accepted", "next_token", "accept_mask", "p_tok", "q_tok", "first_stop", "next_prob", "packed", "_buf")
+    """Outputs of one verify step.  The eight tensors are views of ONE device buffer, created on first access."""
+    __slots__ = ("_buf", "_B", "_g", "_v")
+    _NAMES = ("n_accepted", "next_token", "accept_mask", "p_tok", "q_tok", "first_stop", "next_prob", "packed")
 
-    def __init__(self, outs):
-        (self.n_accepted, self.next_token, self.accept_mask, self.p_tok, self.q_tok, self.first_stop,
-         self.next_prob, self.packed) = outs[:8]
-        self._buf = outs[8] if len(outs) > 8 else None
+    def __init__(self, buf, B, g):
+        self._buf, self._B, self._g, self._v = buf, B, g, None
+
+    def _views(self):
+        if self._v is None:
+            self._v = _verify_views(self._buf, self._B, self._g)
+        return self._v
+
+    n_accepted = property(lambda self: self._views()[0])
+    next_token = property(lambda self: self._views()[1])
+    accept_mask = property(lambda self: self._views()[2])
+    p_tok = property(lambda self: self._views()[3])
+    q_tok = property(lambda self: self._views()[4])
+    first_stop = property(lambda self: self._views()[5])
+    next_prob = property(lambda self: self._views()[6])
+    packed = property(lambda self: self._views()[7])
 
     def host(self):
         """ONE device->host copy (one sync) of everything a decode loop reads per step:
         -> (n_accepted [B], next_token [B], first_stop [B]) as python lists.  The reference pays three `.item()` syncs
         here (sampling/speculative_decoding.py:141-152, 172-187)."""
-        B = self.n_accepted.numel()
-        if self._buf is None:
-            return self.n_accepted.tolist(), self.next_token.tolist(), self.first_stop.tolist()
+        B, g = self._B, self._g
         h = self._buf.cpu()
-        g = self.accept_mask.shape[1] if self.accept_mask.dim() == 2 else 0
-        n32 = 3 * B + 2 * B * g + B * (g + 2)
-        n32 += n32 & 1
+        n32 = _n32(B, g)
         i32 = h[:n32 * 4].view(torch.int32)
         nxt = h[n32 * 4:n32 * 4 + B * 8].view(torch.int64)
         return i32[0:B].tolist(), nxt.tolist(), i32[B:2 * B].tolist()
@@ -343,9 +379,9 @@ def fused_verify(target_logits, draft_logits, draft_tokens, u_accept=None, u_sam
         stop_tokens = None
     # direct call of the implementation (same code the registered torch op `specdec::verify` runs) -- skips
     # the dispatcher's per-call overhead, which matters at small batch
-    return VerifyResult(_verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, int(seed), int(offset),
-                                     int(seq_id0), float(temperature), int(top_k), float(top_p),
-                                     L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
+    return VerifyResult(*_verify_impl(target_logits, draft_logits, draft_tokens, u_accept, u_sample, int(seed), int(offset),
+                                      int(seq_id0), float(temperature), int(top_k), float(top_p),
+                                      L.SAMPLE_GREEDY if greedy else L.SAMPLE_INVCDF, int(flags), stop_tokens))
 
 
 class GraphedVerify:

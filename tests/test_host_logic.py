@@ -146,15 +146,19 @@ def test_all_gather_packed_world2_gloo(tmp_path):
 
 
 def test_bench_reference_arm_contract():
-    """`bench.py --impl reference` prints the contract's JSON line from the CPU port (tiny shape here)."""
+    """`bench.py --impl reference` prints the contract's JSON line (tiny shape here): the unmodified reference from
+    oracle/_ref when that copy exists (build container, GPU box), else the torch port."""
     import json
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0", "--V", "4096", "--cpu-sample-B", "2"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stderr
     d = json.loads(out.stdout.strip().splitlines()[-1])
     assert d["impl"] == "reference" and d["unit"] == "tokens/s" and d["value"] > 0
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    from oracle import ref_arm
+    assert d["cpu_baseline"]["kind"] == ("reference" if ref_arm.available() else "port") and d["cpu_baseline"]["cores"] >= 1
     assert d["e2e"]["h2d_bytes_per_step"] == 0
+    assert d["steps"] == 1 and set(d["config"]) == {"workload", "l2", "parallelism"}
+    assert abs(d["ms_per_step"] - d["ms_per_sample_step"] * 256 / 2) < 1e-6 * d["ms_per_step"]
 
 
 def test_oracle_verify_semantics_small(oracle_mod):

@@ -24,17 +24,17 @@ def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
                         case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
     torch.cuda.synchronize()
     if tgt.shape[0] <= 64:
-        # small batches of the plain modes take the one-launch cluster path (csrc/cluster_small.cuh) by default: every
-        # case is ALSO run through the three-launch pipeline and through 8-CTA clusters; the decisions must be identical
+        # every small case is ALSO run through the opt-in one-launch cluster path (csrc/cluster_small.cuh; 16- and 8-CTA
+        # clusters) and through the pipeline with the atomics + counters tail: the decisions must be identical
         lib = sd._lib.lib()
-        for opts in ({b"small_b": 0}, {b"small_cl": 8}, {b"small_b": 0, b"tail_slots": 0}):
+        for opts in ({b"small_b": 64}, {b"small_b": 64, b"small_cl": 8}, {b"tail_slots": 0}):
             opt = tuple(opts.items())
             for k_, v_ in opts.items():
                 assert lib.specdec_set_option(k_, v_) == 0
             r2 = sd.fused_verify(tgt.to(dev), None if ngram else case["draft"].to(dev), case["draft_tokens"].to(dev),
                                  case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
             torch.cuda.synchronize()
-            assert lib.specdec_set_option(b"small_b", 64) == 0 and lib.specdec_set_option(b"small_cl", 16) == 0
+            assert lib.specdec_set_option(b"small_b", 0) == 0 and lib.specdec_set_option(b"small_cl", 16) == 0
             assert lib.specdec_set_option(b"tail_slots", 1) == 0
             for a in ("n_accepted", "next_token", "accept_mask", "first_stop", "packed"):
                 assert torch.equal(getattr(r, a), getattr(r2, a)), (a, opt)
