@@ -77,6 +77,38 @@ __device__ __forceinline__ float2 cweight2(float2 z, float2 c, float2 negmc) {
   e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
   return e;
 }
+// cweight2() * 2^40, bit for bit: every Horner step is scaled by a power of two (IEEE rounding commutes with such a
+// scaling: no intermediate comes near the subnormal or overflow range -- the polynomial lives in [0.7, 1.5] * 2^40, the
+// result in [2^-85, 2^41]), so the fixed-point weight is __float2ull_rz() of the result without the multiply fix40()
+// needs, and P * 2^60 = (e * 2^40) * (inv * 2^20) feeds fix60() the same way.  Saves 1.5 issue slots per logit in the
+// exact tail (the two elements of a pair are NEIGHBOURS OF ONE ROW here: both halves of the packed registers come out
+// of one 16-bit unpack, where pairing the rows cost a MOV per element).
+#define SPECDEC_S40(x) ((x) * 1099511627776.0f)
+__device__ __forceinline__ float2 cweight2_s40(float2 z, float2 c, float2 negmc) {
+  float2 t = __ffma2_rn(z, c, negmc);
+  t.x = fmaxf(t.x, -125.0f);
+  t.y = fmaxf(t.y, -125.0f);
+  const float2 magic = make_float2(12582912.0f, 12582912.0f);
+  const float2 r = __fadd2_rn(t, magic);
+  const float2 fi = __fadd2_rn(r, make_float2(-12582912.0f, -12582912.0f));  // == r - magic
+  const float2 f = __ffma2_rn(fi, make_float2(-1.0f, -1.0f), t);              // == t - fi (exact product)
+  float2 p = make_float2(SPECDEC_S40(SPECDEC_C5), SPECDEC_S40(SPECDEC_C5));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_S40(SPECDEC_C4), SPECDEC_S40(SPECDEC_C4)));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_S40(SPECDEC_C3), SPECDEC_S40(SPECDEC_C3)));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_S40(SPECDEC_C2), SPECDEC_S40(SPECDEC_C2)));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_S40(SPECDEC_C1), SPECDEC_S40(SPECDEC_C1)));
+  p = __ffma2_rn(p, f, make_float2(SPECDEC_S40(1.0f), SPECDEC_S40(1.0f)));
+  float2 e;
+  e.x = __uint_as_float(__float_as_uint(p.x) + (__float_as_uint(r.x) << 23));
+  e.y = __uint_as_float(__float_as_uint(p.y) + (__float_as_uint(r.y) << 23));
+  return e;
+}
+// residuals of two neighbouring tokens from their scaled weights: max(0, P - Q) * 2^60 each, ready for __float2ull_rz
+// (ip2 = (inv_p, inv_p) * 2^20, niq2 = -(inv_q, inv_q) * 2^20; a + (-Q) rounds exactly like a - Q)
+__device__ __forceinline__ float2 resid2_s60(float4 e, float2 ip2, float2 niq2) {
+  const float2 r = __fadd2_rn(__fmul2_rn(make_float2(e.x, e.y), ip2), __fmul2_rn(make_float2(e.z, e.w), niq2));
+  return make_float2(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f));
+}
 __device__ __forceinline__ u64 fix40(float x) { return __float2ull_rz(__fmul_rn(x, 1099511627776.0f)); }
 __device__ __forceinline__ u64 fix60(float x) { return __float2ull_rz(__fmul_rn(x, 1152921504606846976.0f)); }
 __device__ __forceinline__ unsigned u24_of(float u) {

@@ -456,18 +456,17 @@ __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& 
       job.q_tok[(long long)b * g + prow_i] = row_prob<DT>(rq, qrowp, tok, c);
     }
     // ---- phase B: residual partial sums from the cached weights ----
-    const float2 inv2 = make_float2(invp, invq);
+    const float ip20 = __fmul_rn(invp, 1048576.0f), iq20 = __fmul_rn(invq, 1048576.0f);  // (exact)
+    const float2 ip2 = make_float2(ip20, ip20), niq2 = make_float2(-iq20, -iq20);
     for (int seg = s0 + w; seg < s1; seg += TF_T / 32) {
       const float4* src = ecache + (size_t)(seg - s0) * 128 + lane;
       const int j0 = (seg * 32 + lane) * 8;
       u64 s = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 e = src[k * 32];
-        const float2 a = __fmul2_rn(make_float2(e.x, e.y), inv2);
-        const float2 d = __fmul2_rn(make_float2(e.z, e.w), inv2);
-        const float v0 = fmaxf(__fsub_rn(a.x, a.y), 0.0f), v1 = fmaxf(__fsub_rn(d.x, d.y), 0.0f);
-        s += fix60(v0) + fix60(v1);
+        const float2 rr = resid2_s60(src[k * 32], ip2, niq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
+        const float v0 = rr.x, v1 = rr.y;
+        s += __float2ull_rz(v0) + __float2ull_rz(v1);           // == fix60(max(0, P - Q))
         if (GREEDY) {
           if (j0 + 2 * k < V && v0 > best) { best = v0; bidx = j0 + 2 * k; }
           if (j0 + 2 * k + 1 < V && v1 > best) { best = v1; bidx = j0 + 2 * k + 1; }

@@ -40,14 +40,14 @@ __device__ __forceinline__ void block_sum2_u64(u64& a, u64& b, u64* sh) {
   cta_sync();
 }
 
-// Canonical sums of segments [s0, s1) of a row pair; CACHE: also keep (e_p, e_q) in shared memory as
-// float4 {e_p[2k], e_q[2k], e_p[2k+1], e_q[2k+1]} at [(seg - s0) * 128 + k * 32 + lane] (conflict-free).
+// Canonical sums of segments [s0, s1) of a row pair; CACHE: also keep the weights, SCALED by 2^40 (cweight2_s40), in
+// shared memory as float4 {e_p[2k], e_p[2k+1], e_q[2k], e_q[2k+1]} at [(seg - s0) * 128 + k * 32 + lane] (conflict-free).
 template <int DT, bool CACHE, int NS_ = 0>
 __device__ __forceinline__ void pair_sums(const void* prow, const void* qrow, bool pal, bool qal, int V, float c,
                                           float mcp, float mcq, int s0, int s1, float4* ecache, u64& sp, u64& sq) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int NV = (V + 7) >> 3;
-  const float2 c2 = make_float2(c, c), nmc2 = make_float2(-mcp, -mcq);
+  const float2 c2 = make_float2(c, c), nmp2 = make_float2(-mcp, -mcp), nmq2 = make_float2(-mcq, -mcq);
   constexpr int WPB = TF_T / 32;
   constexpr int NS = NS_ ? NS_ : ((DT == DT_F32) ? 2 : 4);  // segments in flight per warp (raw, still packed loads)
   for (int seg = s0 + w; seg < s1; seg += NS * WPB) {
@@ -68,12 +68,12 @@ __device__ __forceinline__ void pair_sums(const void* prow, const void* qrow, bo
           unpack8<DT>(rp[q], xp);
           unpack8<DT>(rq[q], xq);
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {  // (target, drafter) logit of the same token as one fp32x2 pair
-            const float2 e0 = cweight2(make_float2(xp[2 * k], xq[2 * k]), c2, nmc2);
-            const float2 e1 = cweight2(make_float2(xp[2 * k + 1], xq[2 * k + 1]), c2, nmc2);
-            sp += fix40(e0.x) + fix40(e1.x);
-            sq += fix40(e0.y) + fix40(e1.y);
-            if (CACHE) dst[k * 32] = make_float4(e0.x, e0.y, e1.x, e1.y);
+          for (int k = 0; k < 4; ++k) {  // two neighbouring tokens of one row as one fp32x2 pair, weights * 2^40
+            const float2 ep = cweight2_s40(make_float2(xp[2 * k], xp[2 * k + 1]), c2, nmp2);
+            const float2 eq = cweight2_s40(make_float2(xq[2 * k], xq[2 * k + 1]), c2, nmq2);
+            sp += __float2ull_rz(ep.x) + __float2ull_rz(ep.y);  // == fix40(e): e * 2^40 is exact
+            sq += __float2ull_rz(eq.x) + __float2ull_rz(eq.y);
+            if (CACHE) dst[k * 32] = make_float4(ep.x, ep.y, eq.x, eq.y);
           }
         } else if (CACHE) {
 #pragma unroll
@@ -197,7 +197,8 @@ __device__ __forceinline__ bool tail_item(const DecideJob& job, const HybridWs& 
       job.q_tok[(long long)b * g + prow_i] = row_prob<DT>(rq, qrowp, tok, c);
     }
     // ---- phase B: residual partial sums from the cached weights ----
-    const float2 inv2 = make_float2(invp, invq);
+    const float ip20 = __fmul_rn(invp, 1048576.0f), iq20 = __fmul_rn(invq, 1048576.0f);  // (exact)
+    const float2 ip2 = make_float2(ip20, ip20), niq2 = make_float2(-iq20, -iq20);
     if (w < TF_T / 32)
     for (int seg = s0 + w; seg < s1; seg += TF_T / 32) {
       const float4* src = ecache + (size_t)(seg - s0) * 128 + lane;
@@ -205,11 +206,9 @@ __device__ __forceinline__ bool tail_item(const DecideJob& job, const HybridWs& 
       u64 s = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float4 e = src[k * 32];
-        const float2 a = __fmul2_rn(make_float2(e.x, e.y), inv2);
-        const float2 d = __fmul2_rn(make_float2(e.z, e.w), inv2);
-        const float v0 = fmaxf(__fsub_rn(a.x, a.y), 0.0f), v1 = fmaxf(__fsub_rn(d.x, d.y), 0.0f);
-        s += fix60(v0) + fix60(v1);
+        const float2 rr = resid2_s60(src[k * 32], ip2, niq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
+        const float v0 = rr.x, v1 = rr.y;
+        s += __float2ull_rz(v0) + __float2ull_rz(v1);           // == fix60(max(0, P - Q))
         if (GREEDY) {
           if (j0 + 2 * k < V && v0 > best) { best = v0; bidx = j0 + 2 * k; }
           if (j0 + 2 * k + 1 < V && v1 > best) { best = v1; bidx = j0 + 2 * k + 1; }

@@ -1524,6 +1524,7 @@ static bool pdl_enabled(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
 }
+static int g_tf_balance = 1;     // fused tail: slice sizes rounded to a multiple of 8 segments (one per warp)
 static int g_tail_slots = 1;     // fused tail: inter-CTA exchange through self-validating words (0: atomics + counters)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
 static int g_no_klist = 0;       // test hook: specdec_set_option("no_klist", 1) => masked modes always draw by a sweep over the row
@@ -1835,8 +1836,14 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   HybridWs ws = ws_in;
   // fused tail (tail_fused.cuh): nch CTAs per sequence keep the canonical weights of the deciding row pair
   // in shared memory; needs the slice of one CTA to fit
-  const int nch = g_tf_ch;
-  const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5), spc = (nseg + nch - 1) / nch;
+  const int nseg = ((((rj.V + 7) >> 3) + 31) >> 5);
+  int nch = g_tf_ch, spc = (nseg + nch - 1) / nch;
+  if (g_tf_balance && spc >= 8) {
+    // slices of a multiple of 8 segments: the 8 warps of a CTA get the same number of 256-pair segments (26 segments
+    // per CTA left 6 of the 8 warps idle for a quarter of both phases)
+    spc = ((spc + 4) / 8) * 8;
+    nch = (nseg + spc - 1) / spc;
+  }
   const size_t tf_smem = (size_t)spc * TF_SEG_BYTES;
   bool fused_ok = !masked && dj.gamma > 0 && tf_smem <= 200 * 1024 && !g_no_fused_tail;
   // exchange between the CTAs of a sequence: self-validating words (tail_slots_kernel, default) or atomics + counters
@@ -2242,7 +2249,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_tail_slots = 1; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_tail_slots = 1; g_tf_balance = 1; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2261,6 +2268,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "no_klist")) { g_no_klist = value; return 0; }
   if (!strcmp(name, "small_b")) { g_small_b = value; return 0; }
   if (!strcmp(name, "tail_slots")) { g_tail_slots = value; return 0; }
+  if (!strcmp(name, "tf_balance")) { g_tf_balance = value; return 0; }
   if (!strcmp(name, "small_cl")) { g_small_cl = value; return 0; }
   if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
   if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }
