@@ -104,10 +104,12 @@ __device__ __forceinline__ float2 cweight2_s40(float2 z, float2 c, float2 negmc)
   return e;
 }
 // residuals of two neighbouring tokens from their scaled weights: max(0, P - Q) * 2^60 each, ready for __float2ull_rz
-// (ip2 = (inv_p, inv_p) * 2^20, niq2 = -(inv_q, inv_q) * 2^20; a + (-Q) rounds exactly like a - Q)
-__device__ __forceinline__ float2 resid2_s60(float4 e, float2 ip2, float2 niq2) {
-  const float2 r = __fadd2_rn(__fmul2_rn(make_float2(e.x, e.y), ip2), __fmul2_rn(make_float2(e.z, e.w), niq2));
-  return make_float2(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f));
+// (ip2 = (inv_p, inv_p) * 2^20, iq2 = (inv_q, inv_q) * 2^20).  The subtraction is SCALAR on purpose: ptxas contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 (observed with nvcc 12.9 for sm_100a, -fmad=false notwithstanding), which
+// skips the rounding of Q and changed one emitted token in 256 sequences x 128256 tokens; scalar sub.rn is never fused.
+__device__ __forceinline__ float2 resid2_s60(float4 e, float2 ip2, float2 iq2) {
+  const float2 P = __fmul2_rn(make_float2(e.x, e.y), ip2), Q = __fmul2_rn(make_float2(e.z, e.w), iq2);
+  return make_float2(fmaxf(__fsub_rn(P.x, Q.x), 0.0f), fmaxf(__fsub_rn(P.y, Q.y), 0.0f));
 }
 __device__ __forceinline__ u64 fix40(float x) { return __float2ull_rz(__fmul_rn(x, 1099511627776.0f)); }
 __device__ __forceinline__ u64 fix60(float x) { return __float2ull_rz(__fmul_rn(x, 1152921504606846976.0f)); }

@@ -65,6 +65,9 @@ __device__ __forceinline__ unsigned long long l2_evict_normal_policy() {
   return pol;
 }
 
+#ifndef SPECDEC_POLL_NS
+#define SPECDEC_POLL_NS 40  // pause between polls of the exchange words (tuning builds: -DSPECDEC_POLL_NS=...)
+#endif
 #ifndef MG_NS_V
 #define MG_NS_V 2
 #endif
@@ -344,7 +347,7 @@ __device__ __forceinline__ bool slots_collect(const HybridWs& ws, int b, int S, 
       }
       if (__shfl_sync(0xffffffffu, ab, 0)) return false;
     }
-    __nanosleep(40);
+    __nanosleep(SPECDEC_POLL_NS);
   }
   if (MAXOP) {
 #pragma unroll
@@ -457,14 +460,14 @@ __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& 
     }
     // ---- phase B: residual partial sums from the cached weights ----
     const float ip20 = __fmul_rn(invp, 1048576.0f), iq20 = __fmul_rn(invq, 1048576.0f);  // (exact)
-    const float2 ip2 = make_float2(ip20, ip20), niq2 = make_float2(-iq20, -iq20);
+    const float2 ip2 = make_float2(ip20, ip20), iq2 = make_float2(iq20, iq20);
     for (int seg = s0 + w; seg < s1; seg += TF_T / 32) {
       const float4* src = ecache + (size_t)(seg - s0) * 128 + lane;
       const int j0 = (seg * 32 + lane) * 8;
       u64 s = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 rr = resid2_s60(src[k * 32], ip2, niq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
+        const float2 rr = resid2_s60(src[k * 32], ip2, iq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
         const float v0 = rr.x, v1 = rr.y;
         s += __float2ull_rz(v0) + __float2ull_rz(v1);           // == fix60(max(0, P - Q))
         if (GREEDY) {
@@ -513,7 +516,7 @@ __device__ __forceinline__ bool mega_item(const DecideJob& job, const HybridWs& 
         }
         if (__shfl_sync(0xffffffffu, ab, 0)) { ok = false; break; }
       }
-      __nanosleep(40);
+      __nanosleep(SPECDEC_POLL_NS);
     }
     total = warp_sum_u64(total);
     u64 bk = 0, dummy = 0;

@@ -198,7 +198,7 @@ __device__ __forceinline__ bool tail_item(const DecideJob& job, const HybridWs& 
     }
     // ---- phase B: residual partial sums from the cached weights ----
     const float ip20 = __fmul_rn(invp, 1048576.0f), iq20 = __fmul_rn(invq, 1048576.0f);  // (exact)
-    const float2 ip2 = make_float2(ip20, ip20), niq2 = make_float2(-iq20, -iq20);
+    const float2 ip2 = make_float2(ip20, ip20), iq2 = make_float2(iq20, iq20);
     if (w < TF_T / 32)
     for (int seg = s0 + w; seg < s1; seg += TF_T / 32) {
       const float4* src = ecache + (size_t)(seg - s0) * 128 + lane;
@@ -206,7 +206,7 @@ __device__ __forceinline__ bool tail_item(const DecideJob& job, const HybridWs& 
       u64 s = 0;
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 rr = resid2_s60(src[k * 32], ip2, niq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
+        const float2 rr = resid2_s60(src[k * 32], ip2, iq2);  // max(0, P - Q) * 2^60 of tokens j0 + 2k, j0 + 2k + 1
         const float v0 = rr.x, v1 = rr.y;
         s += __float2ull_rz(v0) + __float2ull_rz(v1);           // == fix60(max(0, P - Q))
         if (GREEDY) {
