@@ -48,6 +48,7 @@ struct HybridWs {
   int* decided;           // [B]     fused tail: set once CTA 0 of the group has decided the sequence
   int* ticket;            // [2]     fused tail: logical CTA ids in dispatch order (one counter per half batch)
   int* abort;             // [1]     set when a bounded inter-CTA wait gave up (see spin_until)
+  int* r_claim;           // [1]     row kernel: next unclaimed row (one counter per chunk); nullptr = static rows
   int* plan_done;         // [B]     megakernel: the sequence's plan record is published
   int* x_next;            // [1]     megakernel: next exact item (sequence-major, claimed in order)
   int* p_next;            // [1]     megakernel: next sequence to plan

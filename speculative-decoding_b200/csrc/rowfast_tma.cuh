@@ -152,6 +152,14 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   __shared__ __align__(8) unsigned long long full_bar[TS_STAGES], empty_bar[TS_STAGES];
   __shared__ float sh_m[2][8], sh_s[2][8], sh_q[2][8], sh_w[2][8];
   __shared__ unsigned sh_i[2][8];
+  // Rows are CLAIMED from a counter (ws.r_claim, zeroed at the head of the call) instead of being assigned by
+  // blockIdx: a CTA that is scheduled late -- another kernel holds a slot of its SM (the NCCL all-gather of the
+  // previous step at 8 GPUs: 176 -> 244 us per step with static rows), or the grid does not divide the rows
+  // (1152 rows on 444 CTAs) -- finds less work left instead of finishing its fixed share alone after everyone else.
+  // The producer publishes each claimed row id in row_id[parity] before the row's first bulk copy (visible to the
+  // consumers through the stage's mbarrier); -1 ends the CTA.  Without a counter (ws.r_claim == nullptr): static rows.
+  __shared__ long long row_id[2];
+  int* const r_claim = ws.r_claim;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
   const int nst = (int)((row_bytes + TS_STAGE_BYTES - 1) / TS_STAGE_BYTES);
@@ -167,17 +175,27 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
       int stage = 0;
       unsigned phase = 0;
       const unsigned long long policy = l2_evict_first_policy();
-      for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
+      int rpar = 0;
+      long long r = r_claim ? (long long)atomicAdd(r_claim, 1) : (long long)blockIdx.x;
+      for (; r < job.R; rpar ^= 1) {
+        // the next claim is issued before this row is streamed: its round trip hides behind 17 bulk copies
+        const long long r_next = r_claim ? (long long)atomicAdd(r_claim, 1) : r + gridDim.x;
         const char* base = (const char*)row_ptr<DT>(job, r);
         for (int k = 0; k < nst; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
+          if (k == 0) row_id[rpar] = r;  // (released to the consumers by the arrive below)
           const unsigned off = (unsigned)k * TS_STAGE_BYTES;
           const unsigned nb = min((unsigned)TS_STAGE_BYTES, row_bytes - off);
           mbar_expect_tx(&full_bar[stage], nb);
           tma_bulk_g2s(ring + stage * TS_STAGE_BYTES, base + off, nb, &full_bar[stage], policy);
           if (++stage == TS_STAGES) { stage = 0; phase ^= 1u; }
         }
+        r = r_next;
       }
+      // no row left: complete one more phase without data so that the consumers wake up and read the end marker
+      mbar_wait(&empty_bar[stage], phase ^ 1u);
+      row_id[rpar] = -1;
+      mbar_arrive(&full_bar[stage]);
     }
     return;
   }
@@ -185,11 +203,14 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   const float c = job.c;
   int stage = 0, par = 0;
   unsigned phase = 0;
-  for (long long r = blockIdx.x; r < job.R; r += gridDim.x, par ^= 1) {
+  for (;; par ^= 1) {
+    mbar_wait(&full_bar[stage], phase);  // first stage of the next row, or the end marker
+    const long long r = *(volatile long long*)&row_id[par];
+    if (r < 0) break;
     float m = -INFINITY, s = 0.0f;
     unsigned first = 0xFFFFFFFFu;  // AMAX: first index of this thread's maximum
     for (int k = 0; k < nst; ++k) {
-      mbar_wait(&full_bar[stage], phase);
+      if (k > 0) mbar_wait(&full_bar[stage], phase);
       const unsigned off = (unsigned)k * TS_STAGE_BYTES;
       const int nvec = (int)(min((unsigned)TS_STAGE_BYTES, row_bytes - off) >> 4);
       const uint4* sp = reinterpret_cast<const uint4*>(ring + stage * TS_STAGE_BYTES);

@@ -1524,6 +1524,7 @@ static bool pdl_enabled(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
 }
+static int g_static_rows = 0;    // row kernel: rows assigned by blockIdx instead of claimed from a counter (test hook)
 static int g_tf_balance = 1;     // fused tail: slice sizes rounded to a multiple of 8 segments (one per warp)
 static int g_tail_slots = 1;     // fused tail: inter-CTA exchange through self-validating words (0: atomics + counters)
 static int g_no_fused_tail = 0;  // test hook: specdec_set_option("no_fused_tail", 1) => exact_rows + sample_partial
@@ -1698,6 +1699,7 @@ static HybridWs ws_pointers(const WsLayout& w, void* workspace, long long B, lon
   h.sm_slots = h.plan_done + B;
   h.r_ticket = h.ntasks + 11;
   h.abort = h.ntasks + 10;   // (ntasks[0..7] / ticket[0..7]: one counter per chunk)
+  h.r_claim = g_static_rows ? nullptr : h.ticket + 8;  // ticket[8..15]: row-claim counter per chunk
   h.x_next = h.ntasks + 8;
   h.p_next = h.ntasks + 9;
   h.rpart = (float2*)(base + w.rpart);
@@ -1935,6 +1937,7 @@ static void sub_job(const DecideJob& dj, const HybridWs& ws, int b0, int nb, int
   w.acc = ws.acc + (size_t)b0 * rps; w.tot = ws.tot + b0; w.best = ws.best + b0;
   w.acc2 = ws.acc2 + (size_t)b0 * 2; w.fin_done = ws.fin_done + b0; w.decided = ws.decided + b0;
   w.ticket = ws.ticket + half;
+  if (ws.r_claim) w.r_claim = ws.r_claim + half;
   w.ntasks = ws.ntasks + half;
   w.tasks = ws.tasks + (size_t)b0 * (g > 0 ? g : 1);
   w.status = ws.status + (size_t)b0 * (g > 0 ? g : 1);
@@ -2249,7 +2252,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_tail_slots = 1; g_tf_balance = 1; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_tail_slots = 1; g_tf_balance = 1; g_static_rows = 0; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2269,6 +2272,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "small_b")) { g_small_b = value; return 0; }
   if (!strcmp(name, "tail_slots")) { g_tail_slots = value; return 0; }
   if (!strcmp(name, "tf_balance")) { g_tf_balance = value; return 0; }
+  if (!strcmp(name, "static_rows")) { g_static_rows = value; return 0; }
   if (!strcmp(name, "small_cl")) { g_small_cl = value; return 0; }
   if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
   if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }
