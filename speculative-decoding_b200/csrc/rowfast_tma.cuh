@@ -156,9 +156,12 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   // blockIdx: a CTA that is scheduled late -- another kernel holds a slot of its SM (the NCCL all-gather of the
   // previous step at 8 GPUs: 176 -> 244 us per step with static rows), or the grid does not divide the rows
   // (1152 rows on 444 CTAs) -- finds less work left instead of finishing its fixed share alone after everyone else.
-  // The producer publishes each claimed row id in row_id[parity] before the row's first bulk copy (visible to the
-  // consumers through the stage's mbarrier); -1 ends the CTA.  Without a counter (ws.r_claim == nullptr): static rows.
-  __shared__ long long row_id[2];
+  // The producer publishes each claimed row id in row_id[row number mod 8] before the row's first bulk copy (visible
+  // to the consumers through the stage's mbarrier); -1 ends the CTA.  The producer is at most TS_STAGES stages, hence
+  // at most TS_STAGES rows (one-stage rows of a tiny vocabulary), ahead of the slowest consumer warp: 8 slots suffice.
+  // Without a counter (ws.r_claim == nullptr): static rows.
+  static_assert(TS_STAGES + 2 <= 8, "row_id ring too small");
+  __shared__ long long row_id[8];
   int* const r_claim = ws.r_claim;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const unsigned row_bytes = (unsigned)job.V * ((DT == DT_F32) ? 4u : 2u);
@@ -177,7 +180,7 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
       const unsigned long long policy = l2_evict_first_policy();
       int rpar = 0;
       long long r = r_claim ? (long long)atomicAdd(r_claim, 1) : (long long)blockIdx.x;
-      for (; r < job.R; rpar ^= 1) {
+      for (; r < job.R; rpar = (rpar + 1) & 7) {
         // the next claim is issued before this row is streamed: its round trip hides behind 17 bulk copies
         const long long r_next = r_claim ? (long long)atomicAdd(r_claim, 1) : r + gridDim.x;
         const char* base = (const char*)row_ptr<DT>(job, r);
@@ -203,9 +206,9 @@ __global__ void __launch_bounds__(TS_THREADS, 4) rowfast_tma_kernel(DecideJob dj
   const float c = job.c;
   int stage = 0, par = 0;
   unsigned phase = 0;
-  for (;; par ^= 1) {
+  for (int rseq = 0;; rseq = (rseq + 1) & 7, par ^= 1) {
     mbar_wait(&full_bar[stage], phase);  // first stage of the next row, or the end marker
-    const long long r = *(volatile long long*)&row_id[par];
+    const long long r = *(volatile long long*)&row_id[rseq];
     if (r < 0) break;
     float m = -INFINITY, s = 0.0f;
     unsigned first = 0xFFFFFFFFu;  // AMAX: first index of this thread's maximum
