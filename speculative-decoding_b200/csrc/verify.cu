@@ -1785,9 +1785,10 @@ static bool ngram_argmax_tma(const RowJob& rj, cudaStream_t st) {
 
 // phase A: row statistics of the job's rows.  limit_ctas > 0 caps the persistent grid per SM.
 template <int DT>
-static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B, int ctas_per_sm, cudaStream_t st,
+static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws_in, int B, int ctas_per_sm, cudaStream_t st,
                                   bool overlap_prev = false) {
   const RowJob& rj = dj.rj;
+  HybridWs ws = ws_in;
   const bool masked = rj.top_k > 0 || rj.use_p;
   cudaError_t e;
   if (masked) return launch_rowstats<DT>(rj, st);
@@ -1810,6 +1811,9 @@ static cudaError_t launch_phase_a(const DecideJob& dj, const HybridWs& ws, int B
     }
     const int per_sm = (ctas_per_sm + 1) < occ ? (ctas_per_sm + 1) : occ;
     const long long cap = (long long)per_sm * num_sms();
+    // rows are claimed from a counter only when a CTA gets more than one (otherwise the claim's round trip is pure
+    // latency: 93 -> 106 us at B = 128, one row per CTA)
+    if (rj.R <= cap) ws.r_claim = nullptr;
     if (overlap_prev && pdl_enabled(st)) {
       // The row kernel of chunk i > 0 depends on nothing the row kernel of chunk i-1 does (other rows, other
       // RowOut records): launched with programmatic stream serialization and NO dependency wait, its CTAs start

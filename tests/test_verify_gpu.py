@@ -27,7 +27,7 @@ def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
         # every small case is ALSO run through the opt-in one-launch cluster path (csrc/cluster_small.cuh; 16- and 8-CTA
         # clusters) and through the pipeline with the atomics + counters tail: the decisions must be identical
         lib = sd._lib.lib()
-        for opts in ({b"small_b": 64}, {b"small_b": 64, b"small_cl": 8}, {b"tail_slots": 0}):
+        for opts in ({b"small_b": 64}, {b"small_b": 64, b"small_cl": 8}, {b"tail_slots": 0}, {b"static_rows": 1}):
             opt = tuple(opts.items())
             for k_, v_ in opts.items():
                 assert lib.specdec_set_option(k_, v_) == 0
@@ -35,7 +35,7 @@ def _run_both(oracle, case, mode, flags=0, stop=(), dev="cuda"):
                                  case["u_accept"].to(dev), case["u_sample"].to(dev), flags=flags, stop_tokens=list(stop), **m)
             torch.cuda.synchronize()
             assert lib.specdec_set_option(b"small_b", 0) == 0 and lib.specdec_set_option(b"small_cl", 16) == 0
-            assert lib.specdec_set_option(b"tail_slots", 1) == 0
+            assert lib.specdec_set_option(b"tail_slots", 1) == 0 and lib.specdec_set_option(b"static_rows", 0) == 0
             for a in ("n_accepted", "next_token", "accept_mask", "first_stop", "packed"):
                 assert torch.equal(getattr(r, a), getattr(r2, a)), (a, opt)
             np.testing.assert_allclose(r2.p_tok.cpu().numpy(), r.p_tok.cpu().numpy(), rtol=1e-5, atol=0)
