@@ -206,10 +206,28 @@ def run_ours(args):
     seq0 = rank * B
 
     pending = []
+    # the all-gather of the packed results: peer-to-peer stores by a kernel of ours over NVLink (dist.PeerGather) when
+    # symmetric memory is available, else one NCCL all-gather per step on NCCL's stream
+    pgather, gather_kind = None, "none (single GPU)"
+    if world > 1:
+        gather_kind = "nccl all_gather_into_tensor, async"
+        if not args.nccl_gather:
+            try:
+                pgather = sd.dist.PeerGather(world * B, g + 2, slots=8)
+                gather_kind = "p2p stores over NVLink by specdec_peer_publish (symmetric memory), reader lags 2 steps"
+            except Exception as ex:
+                print(f"[bench] PeerGather unavailable ({str(ex)[:120]}): NCCL all-gather", file=sys.stderr)
+    pg_step = [0]
 
     def step(i, ev=None):
         t, d = sets[i % nbuf]
         r = sd.fused_verify(t, d, toks[i % nbuf], None, None, seed=2025, offset=i, seq_id0=seq0, **mode)
+        if pgather is not None:
+            k = pg_step[0]
+            pgather.publish(r.packed, k)
+            out = pgather.gathered(k - 2) if k >= 2 else None  # every rank's results of two steps ago, in stream order
+            pg_step[0] = k + 1
+            return out
         if world > 1:
             # the gathered result is global bookkeeping; a rank continues on its own sequences, so the
             # 768-byte all-gather runs on NCCL's stream and overlaps the next verify step
@@ -365,10 +383,24 @@ def run_ours(args):
     strong = None
     if world > 1 and args.scaling == "weak" and Bglob % world == 0:
         Bs_ = Bglob // world
+        spg = None
+        if pgather is not None:
+            try:
+                spg = sd.dist.PeerGather(world * Bs_, g + 2, slots=8)
+            except Exception:
+                spg = None
+        sk = [0]
+
         def sstep(i):
             t, d = sets[i % nbuf]
             r = sd.fused_verify(t[:Bs_], d[:Bs_], toks[i % nbuf][:Bs_], None, None, seed=2025, offset=i,
                                 seq_id0=rank * Bs_, **mode)
+            if spg is not None:
+                spg.publish(r.packed, sk[0])
+                if sk[0] >= 2:
+                    spg.gathered(sk[0] - 2)
+                sk[0] += 1
+                return
             out_, work = sd.dist.all_gather_packed(r.packed, world * Bs_, async_op=True)
             pending.append(work)
             if len(pending) > 32:
@@ -612,7 +644,9 @@ def run_ours(args):
     if rank == 0:
         peak, peak_src = peaks()
         traffic = None
-        tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r2_traffic.json")
+        if not os.path.exists(tp):
+            tp = os.path.join(ROOT, "profiles", "r1_traffic.json")
         if os.path.exists(tp) and dtype == "bf16" and (B, g, V) == (256, 4, 128256):
             try:
                 traffic = float(json.load(open(tp))["rowfast_tma_kernel_dram_bytes_per_launch"])
@@ -627,7 +661,7 @@ def run_ours(args):
             "config": config_dict(args, world),
             "roofline": {"bound": "hbm", "kernel": "rowfast_tma_kernel" if dtype != "f32" else "rowfast_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": ach / peak, "traffic": traffic,
-                         "traffic_source": "ncu --set full capture of one full-batch launch (profiles/r1_traffic.json), dram read+write bytes",
+                         "traffic_source": "ncu --set full capture of one full-batch launch (profiles/r2_traffic.json), dram read+write bytes",
                          "peak_source": peak_src,
                          "alg_bytes_per_launch": ab, "kernel_ms": t_rowstats, "decide_kernel_ms": t_decide,
                          "kernel_timed": ("alone: separate pass with the two-chunk stream pipelining off, one launch "
@@ -639,6 +673,7 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / Ke, "pinned_buffers_numa_node": numa},
             # kernels of ours inside the timed region
             "gpu_launches": int(round(K * per_step)), "gpu_launches_per_step": by_name, "gpu_launches_source": launches_src,
+            "gather": gather_kind,
             "graph_replay_ms_per_step": ms_graph,
             "two_batches_in_flight_ms_per_step": ms_two,
             "clocks": clocks,
@@ -713,6 +748,7 @@ def main():
     ap.add_argument("--cpu-sample-B", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--nccl-gather", action="store_true", help="N>1: all-gather the packed results with NCCL instead of P2P stores")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: B sequences per GPU (default); strong: B is the global batch, sharded across the GPUs")
     args = ap.parse_args()

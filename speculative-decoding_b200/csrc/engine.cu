@@ -168,7 +168,62 @@ __global__ void batch_writeback_kernel(int B, int g, const int* n_accepted, cons
   else if (n_active_out) atomicAdd(n_active_out, 1);
 }
 
+// ---- all-gather of the packed per-sequence results by peer-to-peer stores over NVLink / NVSwitch ----
+// One CTA per peer copies this rank's block of packed int32 words into the peer's gather buffer (plain stores into
+// peer-mapped memory), makes them visible system-wide and then releases the peer's arrival flag of this rank with
+// the step's sequence number.  No NCCL kernel, no host round trip: the launch rides the verify stream right behind
+// the step that produced the words.
+__device__ __forceinline__ void st_release_sys(int* p, int v) {
+  asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_sys(const int* p) {
+  int v;
+  asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__global__ void __launch_bounds__(256) peer_publish_kernel(const int* src, int n_words, int* const* peer_bufs, long long dst_off_words,
+                                                           int* const* peer_flags, long long flag_off_words, int seq) {
+  int* dst = peer_bufs[blockIdx.x] + dst_off_words;
+  if ((((size_t)src | (size_t)dst) & 15) == 0) {
+    const int n4 = n_words >> 2;
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) reinterpret_cast<int4*>(dst)[i] = reinterpret_cast<const int4*>(src)[i];
+    for (int i = (n4 << 2) + threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+  } else {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) st_release_sys(peer_flags[blockIdx.x] + flag_off_words, seq);
+}
+// one warp: lane r waits until rank r's flag of the slot has reached seq (bounded: ~2 s, then *status = 1)
+__global__ void peer_wait_kernel(const int* flags, int world, int seq, int* status) {
+  const int lane = threadIdx.x;
+  bool ok = true;
+  if (lane < world) {
+    ok = false;
+    for (unsigned it = 0; it < (1u << 24); ++it) {
+      if (ld_acquire_sys(flags + lane) - seq >= 0) { ok = true; break; }
+      __nanosleep(100);
+    }
+  }
+  if (!__all_sync(0xffffffffu, ok) && lane == 0 && status) *status = 1;
+}
+
 }  // namespace specdec
+
+extern "C" int specdec_peer_publish(const int32_t* packed_local, int n_words, void* const* peer_bufs_dev, int64_t dst_off_words,
+                                    int world, void* const* peer_flags_dev, int64_t flag_off_words, int32_t seq,
+                                    specdec_stream_t stream) {
+  if (!packed_local || n_words <= 0 || !peer_bufs_dev || !peer_flags_dev || world <= 0 || world > 1024) return SPECDEC_ERR_ARG;
+  specdec::peer_publish_kernel<<<world, 256, 0, (cudaStream_t)stream>>>((const int*)packed_local, n_words, (int* const*)peer_bufs_dev,
+                                                                       dst_off_words, (int* const*)peer_flags_dev, flag_off_words, seq);
+  return (int)cudaGetLastError();
+}
+extern "C" int specdec_peer_wait(const int32_t* flags_local, int world, int32_t seq, int32_t* status, specdec_stream_t stream) {
+  if (!flags_local || world <= 0 || world > 32) return SPECDEC_ERR_ARG;
+  specdec::peer_wait_kernel<<<1, 32, 0, (cudaStream_t)stream>>>((const int*)flags_local, world, seq, (int*)status);
+  return (int)cudaGetLastError();
+}
 
 extern "C" int specdec_topk_ids(const void* logits, int dtype, int64_t rows, int V, int64_t row_stride, int k, int64_t* out_ids,
                                 specdec_stream_t stream) {

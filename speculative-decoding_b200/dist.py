@@ -60,3 +60,61 @@ def all_gather_packed(packed_local: torch.Tensor, total: int, group=None, async_
 def unpack_results(packed: torch.Tensor):
     """-> (n_accepted [B], tokens [B, gamma+1] with -1 padding; tokens[b, n_b] is the next token)"""
     return packed[:, 0], packed[:, 1:]
+
+
+class PeerGather:
+    """All-gather of the packed per-sequence results by peer-to-peer stores over NVLink / NVSwitch issued by ONE tiny
+    kernel of this library (`specdec_peer_publish`, csrc/engine.cu) right behind the verify step on the verify stream:
+    no NCCL kernel competes with the persistent row kernel for an SM slot, no collective is enqueued per step, and the
+    result lands in every rank's gather buffer `latency of one NVLink store + flag` after the step ends.
+
+    The buffers are symmetric memory (torch.distributed._symmetric_memory: peer-mapped allocations exchanged once at
+    construction, the only collective this class ever runs).  A ring of `slots` buffers lets a rank run up to
+    `slots - 1` steps ahead of the slowest reader; `gathered(step)` enqueues a one-warp wait for that step's arrival
+    flags on the current stream and returns the [total, width] view.
+    """
+
+    def __init__(self, total: int, width: int, group=None, slots: int = 8, device=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib as L
+        self._L = L
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        self.total, self.width, self.slots = int(total), int(width), int(slots)
+        dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.lo, self.hi = shard_range(self.total, self.rank, self.world)
+        self.buf = symm.empty((self.slots, self.total, self.width), dtype=torch.int32, device=dev)
+        self.flags = symm.empty((self.slots, max(self.world, 4)), dtype=torch.int32, device=dev)
+        self.buf.fill_(-1)
+        self.flags.zero_()
+        torch.cuda.synchronize(dev)
+        hb = symm.rendezvous(self.buf, grp.group_name)
+        hf = symm.rendezvous(self.flags, grp.group_name)
+        self._peer_bufs = torch.tensor([int(p) for p in hb.buffer_ptrs], dtype=torch.int64, device=dev)
+        self._peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._handles = (hb, hf)
+        dist.barrier(grp)
+        torch.cuda.synchronize(dev)
+
+    def _slot_seq(self, step: int):
+        return step % self.slots, step // self.slots + 1
+
+    def publish(self, packed_local: torch.Tensor, step: int) -> None:
+        """packed_local: this rank's int32 [hi - lo, width] rows of step `step` (contiguous, CUDA)."""
+        if packed_local.dtype != torch.int32 or not packed_local.is_contiguous() or packed_local.numel() != (self.hi - self.lo) * self.width:
+            raise ValueError("PeerGather.publish: expected the rank's contiguous int32 [rows, width] block")
+        slot, seq = self._slot_seq(step)
+        rc = self._L.lib().specdec_peer_publish(
+            packed_local.data_ptr(), packed_local.numel(), self._peer_bufs.data_ptr(),
+            (slot * self.total + self.lo) * self.width, self.world, self._peer_flags.data_ptr(),
+            slot * self.flags.shape[1] + self.rank, seq, torch.cuda.current_stream().cuda_stream)
+        self._L.check(rc, "specdec_peer_publish")
+
+    def gathered(self, step: int) -> torch.Tensor:
+        """[total, width] results of every rank for `step`, valid in stream order after this call."""
+        slot, seq = self._slot_seq(step)
+        rc = self._L.lib().specdec_peer_wait(self.flags[slot].data_ptr(), self.world, seq, self.status.data_ptr(),
+                                             torch.cuda.current_stream().cuda_stream)
+        self._L.check(rc, "specdec_peer_wait")
+        return self.buf[slot]
