@@ -224,8 +224,7 @@ def run_ours(args):
         r = sd.fused_verify(t, d, toks[i % nbuf], None, None, seed=2025, offset=i, seq_id0=seq0, **mode)
         if pgather is not None:
             k = pg_step[0]
-            pgather.publish(r.packed, k)
-            out = pgather.gathered(k - 2) if k >= 2 else None  # every rank's results of two steps ago, in stream order
+            out = pgather.publish(r.packed, k, k - 2)  # + every rank's results of two steps ago, in stream order
             pg_step[0] = k + 1
             return out
         if world > 1:
@@ -396,9 +395,7 @@ def run_ours(args):
             r = sd.fused_verify(t[:Bs_], d[:Bs_], toks[i % nbuf][:Bs_], None, None, seed=2025, offset=i,
                                 seq_id0=rank * Bs_, **mode)
             if spg is not None:
-                spg.publish(r.packed, sk[0])
-                if sk[0] >= 2:
-                    spg.gathered(sk[0] - 2)
+                spg.publish(r.packed, sk[0], sk[0] - 2)
                 sk[0] += 1
                 return
             out_, work = sd.dist.all_gather_packed(r.packed, world * Bs_, async_op=True)

@@ -232,11 +232,13 @@ SPECDEC_API int specdec_batch_writeback(int B, int gamma, const int32_t* n_accep
  * buffer / flag array (peer-mapped, e.g. torch.distributed._symmetric_memory).  specdec_peer_publish copies
  * packed_local[0, n_words) to peer_bufs[p] + dst_off_words for every p, then releases peer_flags[p][flag_off_words]
  * = seq; specdec_peer_wait (one warp) returns on the stream once flags_local[r] >= seq for every r < world
- * (*status = 1 after a bounded wait).  Both ride the caller's stream; neither touches the host.
+ * (*status = 1 after a bounded wait).  wait_flags_local != NULL makes specdec_peer_publish ALSO perform that wait (for
+ * an earlier step's slot, wait_seq) in an extra CTA of the same launch.  Both ride the caller's stream; neither touches
+ * the host.
  */
 SPECDEC_API int specdec_peer_publish(const int32_t* packed_local, int n_words, void* const* peer_bufs_dev, int64_t dst_off_words,
                          int world, void* const* peer_flags_dev, int64_t flag_off_words, int32_t seq,
-                         specdec_stream_t stream);
+                         const int32_t* wait_flags_local, int32_t wait_seq, int32_t* status, specdec_stream_t stream);
 SPECDEC_API int specdec_peer_wait(const int32_t* flags_local, int world, int32_t seq, int32_t* status, specdec_stream_t stream);
 
 #ifdef __cplusplus

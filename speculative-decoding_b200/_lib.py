@@ -44,7 +44,7 @@ _SIGS = {
     "specdec_ngram_has_gram": (_i, [_vp, _vp, _vp, _vp, _i, _i64, _vp, _vp]),
     "specdec_ngram_seed": (_i, [_vp, _u64]),
     "specdec_topk_ids": (_i, [_vp, _i, _i64, _i, _i64, _i, _vp, _vp]),
-    "specdec_peer_publish": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _i, _vp]),
+    "specdec_peer_publish": (_i, [_vp, _i, _vp, _i64, _i, _vp, _i64, _i, _vp, _i, _vp, _vp]),
     "specdec_peer_wait": (_i, [_vp, _i, _i, _vp, _vp]),
     "specdec_batch_writeback": (_i, [_i, _i, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _vp, _vp, _i, _vp, _vp]),
 }

@@ -182,7 +182,26 @@ __device__ __forceinline__ int ld_acquire_sys(const int* p) {
   return v;
 }
 __global__ void __launch_bounds__(256) peer_publish_kernel(const int* src, int n_words, int* const* peer_bufs, long long dst_off_words,
-                                                           int* const* peer_flags, long long flag_off_words, int seq) {
+                                                           int* const* peer_flags, long long flag_off_words, int seq, int world,
+                                                           const int* wait_flags, int wait_seq, int* status) {
+  if ((int)blockIdx.x == world) {
+    // optional extra CTA: the reader side of an EARLIER step (one launch instead of two per step) -- lane r waits until
+    // rank r's flag of that step's slot has reached wait_seq
+    if (threadIdx.x < 32) {
+      bool ok = true;
+      if ((int)threadIdx.x < world) {
+        ok = false;
+        for (unsigned it = 0; it < (1u << 24); ++it) {
+          int v;
+          asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(wait_flags + threadIdx.x) : "memory");
+          if (v - wait_seq >= 0) { ok = true; break; }
+          __nanosleep(100);
+        }
+      }
+      if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0 && status) *status = 1;
+    }
+    return;
+  }
   int* dst = peer_bufs[blockIdx.x] + dst_off_words;
   if ((((size_t)src | (size_t)dst) & 15) == 0) {
     const int n4 = n_words >> 2;
@@ -213,10 +232,11 @@ __global__ void peer_wait_kernel(const int* flags, int world, int seq, int* stat
 
 extern "C" int specdec_peer_publish(const int32_t* packed_local, int n_words, void* const* peer_bufs_dev, int64_t dst_off_words,
                                     int world, void* const* peer_flags_dev, int64_t flag_off_words, int32_t seq,
-                                    specdec_stream_t stream) {
-  if (!packed_local || n_words <= 0 || !peer_bufs_dev || !peer_flags_dev || world <= 0 || world > 1024) return SPECDEC_ERR_ARG;
-  specdec::peer_publish_kernel<<<world, 256, 0, (cudaStream_t)stream>>>((const int*)packed_local, n_words, (int* const*)peer_bufs_dev,
-                                                                       dst_off_words, (int* const*)peer_flags_dev, flag_off_words, seq);
+                                    const int32_t* wait_flags_local, int32_t wait_seq, int32_t* status, specdec_stream_t stream) {
+  if (!packed_local || n_words <= 0 || !peer_bufs_dev || !peer_flags_dev || world <= 0 || world > 32) return SPECDEC_ERR_ARG;
+  specdec::peer_publish_kernel<<<world + (wait_flags_local ? 1 : 0), 256, 0, (cudaStream_t)stream>>>(
+      (const int*)packed_local, n_words, (int* const*)peer_bufs_dev, dst_off_words, (int* const*)peer_flags_dev, flag_off_words, seq,
+      world, (const int*)wait_flags_local, wait_seq, (int*)status);
   return (int)cudaGetLastError();
 }
 extern "C" int specdec_peer_wait(const int32_t* flags_local, int world, int32_t seq, int32_t* status, specdec_stream_t stream) {

@@ -93,6 +93,7 @@ class PeerGather:
         self._peer_bufs = torch.tensor([int(p) for p in hb.buffer_ptrs], dtype=torch.int64, device=dev)
         self._peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._flags_ptr = self.flags.data_ptr()
         self._handles = (hb, hf)
         dist.barrier(grp)
         torch.cuda.synchronize(dev)
@@ -100,16 +101,22 @@ class PeerGather:
     def _slot_seq(self, step: int):
         return step % self.slots, step // self.slots + 1
 
-    def publish(self, packed_local: torch.Tensor, step: int) -> None:
-        """packed_local: this rank's int32 [hi - lo, width] rows of step `step` (contiguous, CUDA)."""
+    def publish(self, packed_local: torch.Tensor, step: int, wait_step: int = -1):
+        """packed_local: this rank's int32 [hi - lo, width] rows of step `step` (contiguous, CUDA).  wait_step >= 0: the
+        same launch also waits (in stream order) for every rank's results of that EARLIER step and their [total, width]
+        view is returned -- one kernel per step for a reader that lags the writers."""
         if packed_local.dtype != torch.int32 or not packed_local.is_contiguous() or packed_local.numel() != (self.hi - self.lo) * self.width:
             raise ValueError("PeerGather.publish: expected the rank's contiguous int32 [rows, width] block")
         slot, seq = self._slot_seq(step)
         rc = self._L.lib().specdec_peer_publish(
             packed_local.data_ptr(), packed_local.numel(), self._peer_bufs.data_ptr(),
             (slot * self.total + self.lo) * self.width, self.world, self._peer_flags.data_ptr(),
-            slot * self.flags.shape[1] + self.rank, seq, torch.cuda.current_stream().cuda_stream)
+            slot * self.flags.shape[1] + self.rank, seq,
+            (self._flags_ptr + 4 * (wait_step % self.slots) * self.flags.shape[1]) if wait_step >= 0 else None,
+            (wait_step // self.slots + 1) if wait_step >= 0 else 0, self.status.data_ptr(),
+            torch.cuda.current_stream().cuda_stream)
         self._L.check(rc, "specdec_peer_publish")
+        return self.buf[wait_step % self.slots] if wait_step >= 0 else None
 
     def gathered(self, step: int) -> torch.Tensor:
         """[total, width] results of every rank for `step`, valid in stream order after this call."""

@@ -28,6 +28,11 @@ for step in range(11):  # wraps the ring of 4 slots twice
     assert torch.equal(got, full), (rank, step)
     ref = sdd.all_gather_packed(full[lo:hi].contiguous(), total)
     assert torch.equal(ref, full)
+    if step >= 1:  # the fused form: publish step s and read step s - 1 in one launch (here: re-publish the same rows)
+        prev = pg.publish(full[lo:hi].contiguous(), step, step - 1)
+        torch.cuda.synchronize()
+        gp = torch.Generator().manual_seed(100 + step - 1)
+        assert torch.equal(prev, torch.randint(-1, 1000, (total, width), generator=gp, dtype=torch.int32).cuda())
     dist.barrier()  # (a reader is done with the slot before anyone can wrap around to it)
 assert int(pg.status[0]) == 0
 dist.barrier()
