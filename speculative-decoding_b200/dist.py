@@ -74,7 +74,10 @@ class PeerGather:
     flags on the current stream and returns the [total, width] view.
     """
 
-    def __init__(self, total: int, width: int, group=None, slots: int = 8, device=None):
+    def __init__(self, total: int, width: int, group=None, slots: int = 8, device=None, overlap: bool = False):
+        """overlap=True: the publish kernel runs on a side stream of this object behind an event recorded on the caller's
+        stream (as NCCL's own stream does), so it never sits on the verify stream's critical path; call
+        `sync_reader()` before consuming a gathered view on the caller's stream."""
         import torch.distributed._symmetric_memory as symm
         from . import _lib as L
         self._L = L
@@ -94,6 +97,9 @@ class PeerGather:
         self._peer_flags = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64, device=dev)
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
         self._flags_ptr = self.flags.data_ptr()
+        self.side = torch.cuda.Stream(device=dev) if overlap else None
+        self._ev = [torch.cuda.Event() for _ in range(4)] if overlap else None
+        self._keep = [None] * 4  # the published blocks stay referenced until the side stream has certainly read them
         self._handles = (hb, hf)
         dist.barrier(grp)
         torch.cuda.synchronize(dev)
@@ -108,15 +114,26 @@ class PeerGather:
         if packed_local.dtype != torch.int32 or not packed_local.is_contiguous() or packed_local.numel() != (self.hi - self.lo) * self.width:
             raise ValueError("PeerGather.publish: expected the rank's contiguous int32 [rows, width] block")
         slot, seq = self._slot_seq(step)
+        stream = torch.cuda.current_stream().cuda_stream
+        if self.side is not None:
+            ev = self._ev[step & 3]
+            ev.record()
+            self.side.wait_event(ev)
+            self._keep[step & 3] = packed_local
+            stream = self.side.cuda_stream
         rc = self._L.lib().specdec_peer_publish(
             packed_local.data_ptr(), packed_local.numel(), self._peer_bufs.data_ptr(),
             (slot * self.total + self.lo) * self.width, self.world, self._peer_flags.data_ptr(),
             slot * self.flags.shape[1] + self.rank, seq,
             (self._flags_ptr + 4 * (wait_step % self.slots) * self.flags.shape[1]) if wait_step >= 0 else None,
-            (wait_step // self.slots + 1) if wait_step >= 0 else 0, self.status.data_ptr(),
-            torch.cuda.current_stream().cuda_stream)
+            (wait_step // self.slots + 1) if wait_step >= 0 else 0, self.status.data_ptr(), stream)
         self._L.check(rc, "specdec_peer_publish")
         return self.buf[wait_step % self.slots] if wait_step >= 0 else None
+
+    def sync_reader(self) -> None:
+        """overlap mode: the caller's stream waits for everything published / awaited so far on the side stream."""
+        if self.side is not None:
+            torch.cuda.current_stream().wait_stream(self.side)
 
     def gathered(self, step: int) -> torch.Tensor:
         """[total, width] results of every rank for `step`, valid in stream order after this call."""

@@ -36,6 +36,18 @@ for step in range(11):  # wraps the ring of 4 slots twice
     dist.barrier()  # (a reader is done with the slot before anyone can wrap around to it)
 assert int(pg.status[0]) == 0
 dist.barrier()
+# overlap mode: the publish kernel rides a side stream behind an event on the caller's stream
+po = sdd.PeerGather(total, width, slots=4, overlap=True)
+for step in range(6):
+    g = torch.Generator().manual_seed(500 + step)
+    full = torch.randint(-1, 1000, (total, width), generator=g, dtype=torch.int32).cuda()
+    po.publish(full[lo:hi].contiguous(), step, step)
+    po.sync_reader()
+    torch.cuda.synchronize()
+    assert torch.equal(po.buf[step % 4], full), (rank, step)
+    dist.barrier()
+assert int(po.status[0]) == 0
+dist.barrier()
 dist.destroy_process_group()
 print("ok", rank)
 """
