@@ -388,7 +388,7 @@ def run_ours(args):
         spg = None
         if pgather is not None:
             try:
-                spg = sd.dist.PeerGather(world * Bs_, g + 2, slots=8)
+                spg = sd.dist.PeerGather(world * Bs_, g + 2, slots=8, overlap=True)
             except Exception:
                 spg = None
         sk = [0]
@@ -418,14 +418,18 @@ def run_ours(args):
             pending.append(work)
             if len(pending) > 32:
                 pending.pop(0).wait()
+        def sdrain():
+            drain()
+            if spg is not None:
+                spg.sync_reader()
         for i in range(5):
             sstep(i)
-        drain()
+        sdrain()
         sync_all()
         e0.record()
         for i in range(K):
             sstep(i)
-        drain()
+        sdrain()
         e1.record()
         sync_all()
         tt = torch.tensor([e0.elapsed_time(e1)], device=dev)
