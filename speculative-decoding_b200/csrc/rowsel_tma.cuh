@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
           o.inv = __fdiv_rn(1.0f, __fmul_rn(__ull2float_rn(Sfix), 0x1p-40f));
         }
         job.out[mt.r] = o;
+        if (!ok && job.n_unres) atomicAdd(job.n_unres, 1);
       }
       __syncwarp();
       __threadfence_block();
@@ -252,13 +253,15 @@ __global__ void __launch_bounds__(RS2_THREADS, 2) rowsel_tma_kernel(RowJob job) 
     int* cj = (int*)(cz + RS2_CAP);
     if (ok && m1 >= th) {
       // my slice holds candidates: look at stage k1 (and k2, k3 if their maxima reach th) again -- from L2, the row
-      // was streamed microseconds ago; a fourth hot stage is left to the fallback kernels
-      if (m4 >= th) s_ovf[par] = 1;
+      // was streamed microseconds ago.  More than three hot stages (2 % of the top-50 rows): this thread looks at ALL
+      // its stages again -- a dozen microseconds for that row's epilogue, instead of leaving the whole row to the
+      // exact fallback kernel (one 512-thread CTA sweeping it twice: 57 us on the critical path of every step)
+      const bool all_stages = (m4 >= th);
       const char* row = (const char*)row_ptr<DT>(job, r);
-      const int nlook = (m3 >= th) ? 3 : ((m2 >= th) ? 2 : 1);
+      const int nlook = all_stages ? nst : ((m3 >= th) ? 3 : ((m2 >= th) ? 2 : 1));
       constexpr int VPT = RS2_STAGE_BYTES / 16 / RS2_CONSUMERS;
       for (int which = 0; which < nlook; ++which) {
-        const int kk = which == 0 ? k1 : (which == 1 ? k2 : k3);
+        const int kk = all_stages ? which : (which == 0 ? k1 : (which == 1 ? k2 : k3));
         uint4 a[VPT];
         int vv[VPT];
 #pragma unroll

@@ -47,6 +47,8 @@ struct RowJob {
   int pre_stats;      // nucleus_fast_kernel: max / MUFU mass / candidate threshold come from rowfast_tma_kernel<DT, 1>
   int2* klist;        // nullable: [R][KL_MAX] (logit bits, index) of the kept tokens of rows whose kept set is small;
                       // the count sits in RowOut.flags bits 8..15 (0 = no list).  Feeds sample_lists_kernel.
+  int* n_unres;       // nullable: rows rowsel_tma_kernel left unresolved (zeroed at the head of the call); the exact
+                      // fallback kernels return at once when it is 0 instead of polling every row's flag
 };
 constexpr int KL_MAX = 64;
 
@@ -448,6 +450,7 @@ __global__ void __launch_bounds__(RS_NT, 2) rowstats_kernel(RowJob job_in) {
   const int V = job.V;
   const float c = job.c;
   constexpr bool masked = HK || HP;
+  if (job.skip_resolved && job.n_unres && __ldcg(job.n_unres) == 0) return;  // rowsel_tma_kernel resolved every row
   for (long long r = blockIdx.x; r < job.R; r += gridDim.x) {
     if (job.skip_resolved && (job.out[r].flags & 1)) continue;  // done by rowsel_tma_kernel / nucleus_fast_kernel (block-uniform)
     const void* row = row_ptr<DT>(job, r);
@@ -1564,6 +1567,7 @@ static int fill_rowjob(RowJob& rj, const void* tgt, const void* drf, long long t
   rj.skip_resolved = 0;
   rj.pre_stats = 0;
   rj.klist = nullptr;
+  rj.n_unres = nullptr;
   return 0;
 }
 
@@ -2201,6 +2205,7 @@ int specdec_verify(const void* target_logits, const void* draft_logits, int dtyp
                        temperature, top_k, top_p, R, workspace, workspace_bytes);
   if (rc) return rc;
   if (!ngram && !g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
+  if (!ngram) dj.rj.n_unres = ws_pointers(wl, workspace, B, R).ntasks + 14;  // (a word of the region zeroed per call)
   dj.draft_tokens = (const long long*)draft_tokens; dj.u_accept = u_accept; dj.u_sample = u_sample;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.seq0 = seq_id0; dj.gamma = gamma;
   dj.offset_dev = nullptr;
@@ -2356,6 +2361,7 @@ int specdec_sample_rows(const void* logits, int dtype, int64_t rows, int V, int6
   if (rc) return rc;
   int* scratch = (int*)((char*)workspace + wl.total);
   if (!g_no_klist) dj.rj.klist = (int2*)((char*)workspace + wl.klist);
+  dj.rj.n_unres = ws_pointers(wl, workspace, rows, rows).ntasks + 14;
   dj.draft_tokens = nullptr; dj.u_accept = nullptr; dj.u_sample = u;
   dj.seed = philox_seed; dj.offset = philox_offset; dj.offset_dev = nullptr; dj.seq0 = seq_id0; dj.gamma = 0;
   dj.greedy = (sample_mode == SPECDEC_SAMPLE_GREEDY); dj.flags = 0; dj.stop = nullptr; dj.n_stop = 0;
