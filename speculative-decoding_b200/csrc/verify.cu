@@ -1623,14 +1623,19 @@ static cudaError_t launch_rowstats(const RowJob& rj, cudaStream_t st) {
   if (!masked) { RS_LAUNCH(false, false, rj); return cudaGetLastError(); }
   // Fast route: rowsel_tma_kernel (one streamed pass + gather of the hot slices + exact selection by a selector warp);
   // the rows it leaves unresolved go to the exact kernels below, which skip every row already flagged.
+  // (n_unres counts the rows rowsel_tma_kernel left: it only means something when that kernel ran, and for pure top-p
+  // the rows pass through two more resolvers before the fallback -- there the fallback polls the flags as before)
   RowJob left = rj;
   if (rj.top_k > 0 && rj.use_p) {
     if (launch_rowsel<DT, true, true>(rj, st)) left.skip_resolved = 1;
+    else left.n_unres = nullptr;
     RS_LAUNCH(true, true, left);
   } else if (rj.top_k > 0) {
     if (launch_rowsel<DT, true, false>(rj, st)) left.skip_resolved = 1;
+    else left.n_unres = nullptr;
     RS_LAUNCH(true, false, left);
   } else {
+    left.n_unres = nullptr;
     if (!g_no_fast_nucleus) {
       cudaError_t e;
       if (!launch_rowsel<DT, false, true>(rj, st)) {
