@@ -21,9 +21,15 @@
 constexpr int RS2_CONSUMERS = 256;
 constexpr int RS2_SELECTORS = 1;  // selector warps (2: one per candidate buffer -- measured slower: 352 vs 310 us on top-k + top-p)
 constexpr int RS2_THREADS = RS2_CONSUMERS + 32 + 32 * RS2_SELECTORS;  // + producer warp + selector warp(s)
-constexpr int RS2_STAGES = 4;
+#ifndef RS2_STAGES_V
+#define RS2_STAGES_V 4
+#endif
+#ifndef RS2_CAP_V
+#define RS2_CAP_V 1024
+#endif
+constexpr int RS2_STAGES = RS2_STAGES_V;
 constexpr int RS2_STAGE_BYTES = 16384;
-constexpr int RS2_CAP = 1024;  // candidates per buffer (== WARP_SELECT_MAX: one warp selects)
+constexpr int RS2_CAP = RS2_CAP_V;  // candidates per buffer (<= WARP_SELECT_MAX: one warp selects)
 constexpr size_t RS2_CAND_BYTES = (size_t)RS2_CAP * (sizeof(float) + sizeof(int) + sizeof(u64));
 constexpr size_t RS2_SMEM = (size_t)RS2_STAGES * RS2_STAGE_BYTES + 2 * RS2_CAND_BYTES;
 
