@@ -748,17 +748,17 @@ __global__ void __launch_bounds__(PT, 4) sample_partial_kernel(DecideJob job, Hy
 // handled sequences set it to CH so that kernel's CTAs return at once).
 // ---------------------------------------------------------------------------------------------
 constexpr int SL_WARPS = 8;
+struct ListSh {  // per-warp scratch of sample_lists_sequence
+  int j[KL_MAX];
+  float p[KL_MAX];
+  u64 w[KL_MAX];
+  int qj[KL_MAX];
+  float qz[KL_MAX];
+};
+// one WARP: the draw of sequence b from the kept-token lists (see sample_lists_kernel)
 template <int DT>
-__global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob job, HybridWs ws, int B) {
-  __shared__ int s_j[SL_WARPS][KL_MAX];
-  __shared__ float s_p[SL_WARPS][KL_MAX];
-  __shared__ u64 s_w[SL_WARPS][KL_MAX];
-  __shared__ int s_qj[SL_WARPS][KL_MAX];
-  __shared__ float s_qz[SL_WARPS][KL_MAX];
-  grid_dependency_wait();
-  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int b = blockIdx.x * SL_WARPS + wib;
-  if (b >= B) return;
+__device__ __forceinline__ void sample_lists_sequence(const DecideJob& job, const HybridWs& ws, const int b, ListSh& lsh) {
+  const int lane = threadIdx.x & 31;
   const RowJob& rj = job.rj;
   const int g = job.gamma, V = rj.V, rps = rj.nT + rj.nD;
   const int n = ws.samp[b * SAMP_N + 0], mode = ws.samp[b * SAMP_N + 1], prow = ws.samp[b * SAMP_N + 2];
@@ -773,7 +773,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob j
   const bool greedy = job.greedy != 0;
   const float us = job.u_sample ? job.u_sample[b]
                                 : philox_uniform(job.seed, job_offset(job), (unsigned)(job.seq0 + b), (unsigned)job.lane_sample);
-  int* sj = s_j[wib]; float* sp = s_p[wib]; u64* sw = s_w[wib]; int* sqj = s_qj[wib]; float* sqz = s_qz[wib];
+  int* sj = lsh.j; float* sp = lsh.p; u64* sw = lsh.w; int* sqj = lsh.qj; float* sqz = lsh.qz;
   // ---- load the lists; the target row's list sorted by token index (rank sort: KL_MAX^2 / 32 comparisons per lane)
   const int2* lp = rj.klist + r1 * KL_MAX;
   int2 e[2];
@@ -809,7 +809,7 @@ __global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob j
         w = fix40(val);
       }
       e[h].x = rank;  // (reuse: destination slot)
-      s_w[wib][rank] = w;
+      sw[rank] = w;
       sp[rank] = val;
     }
   }
@@ -899,6 +899,32 @@ __global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob j
     }
     ws.part_done[b] = CH;  // handled: sample_partial_kernel's CTAs of this sequence return at once
   }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(SL_WARPS * 32) sample_lists_kernel(DecideJob job, HybridWs ws, int B) {
+  __shared__ ListSh lsh[SL_WARPS];
+  grid_dependency_wait();
+  const int wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * SL_WARPS + wib;
+  if (b >= B) return;
+  sample_lists_sequence<DT>(job, ws, b, lsh[wib]);
+}
+
+// plan + draw from the kept-token lists in ONE launch (masked modes with lists: the plan has no exact tasks there, so
+// the sequence is decided by plan_sequence and the same warp can draw right away -- one launch and ~8 us less per step)
+template <int DT>
+__global__ void __launch_bounds__(256) plan_lists_kernel(DecideJob job, HybridWs ws) {
+  __shared__ ListSh lsh[8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  grid_dependency_wait();
+  const int wib = threadIdx.x >> 5;
+  const int b = blockIdx.x * (blockDim.x >> 5) + wib;
+  if (b >= (int)(job.rj.R / (job.rj.nT + job.rj.nD))) return;
+  plan_sequence<DT>(job, ws, b);
+  __syncwarp();
+  __threadfence();
+  if (__ldcg(&ws.seq_tasks[b]) == 0) sample_lists_sequence<DT>(job, ws, b, lsh[wib]);  // (decided by the plan itself)
 }
 
 #include "tail_fused.cuh"

@@ -1527,6 +1527,7 @@ static bool pdl_enabled(cudaStream_t st) {
   cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
   return cudaStreamIsCapturing(st, &cs) == cudaSuccess && cs == cudaStreamCaptureStatusNone;
 }
+static int g_split_lists = 0;    // masked modes: plan and the kept-token-list draw as two launches (test hook)
 static int g_static_rows = 0;    // row kernel: rows assigned by blockIdx instead of claimed from a counter (test hook)
 static int g_tf_balance = 1;     // fused tail: slice sizes rounded to a multiple of 8 segments (one per warp)
 static int g_tail_slots = 1;     // fused tail: inter-CTA exchange through self-validating words (0: atomics + counters)
@@ -1912,11 +1913,18 @@ static cudaError_t launch_phase_b(const DecideJob& dj, const HybridWs& ws_in, in
   cfg.stream = st; cfg.attrs = pdl; cfg.numAttrs = 1; cfg.dynamicSmemBytes = 0;
   cudaError_t e;
   cfg.gridDim = dim3((unsigned)((B + 7) / 8)); cfg.blockDim = dim3(256);
-  if ((e = cudaLaunchKernelEx(&cfg, plan_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  // masked modes with kept-token lists: the plan decides every sequence itself (no exact tasks), so the same warp draws
+  // from the lists right away (plan_lists_kernel); "split_lists" = 1 keeps the two launches (test hook)
+  const bool lists = masked && rj.klist != nullptr;
+  if (lists && !g_split_lists) {
+    if ((e = cudaLaunchKernelEx(&cfg, plan_lists_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  } else {
+    if ((e = cudaLaunchKernelEx(&cfg, plan_kernel<DT>, dj, ws)) != cudaSuccess) return e;
+  }
   cfg.gridDim = dim3((unsigned)B, CH); cfg.blockDim = dim3(PT);
   if (!masked && dj.gamma > 0)  // tasks are looped over
     if ((e = cudaLaunchKernelEx(&cfg, exact_rows_kernel<DT>, dj, ws)) != cudaSuccess) return e;
-  if (masked && rj.klist) {  // sequences whose deciding rows carry kept-token lists are drawn without a sweep
+  if (lists && g_split_lists) {  // sequences whose deciding rows carry kept-token lists are drawn without a sweep
     cfg.gridDim = dim3((unsigned)((B + SL_WARPS - 1) / SL_WARPS)); cfg.blockDim = dim3(SL_WARPS * 32);
     if ((e = cudaLaunchKernelEx(&cfg, sample_lists_kernel<DT>, dj, ws, B)) != cudaSuccess) return e;
     cfg.gridDim = dim3((unsigned)B, CH); cfg.blockDim = dim3(PT);
@@ -2266,7 +2274,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "reset")) {  // every option back to its default (tests call this after each case)
     g_force_ldg = 0; g_chunks = 2; g_chunk0_pct = 50; g_p1_ctas = 3; g_tf_ch = TF_CH_DEFAULT; g_no_fast_nucleus = 0;
     g_no_hist_nucleus = 0; g_no_tma_nucleus = 1; g_no_fast_ngram = 0; g_no_fused_tail = 0; g_no_pdl = 0; g_tma_ngram = 1;
-    g_no_klist = 0; g_tail_slots = 1; g_tf_balance = 1; g_static_rows = 0; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
+    g_no_klist = 0; g_tail_slots = 1; g_tf_balance = 1; g_static_rows = 0; g_split_lists = 0; g_small_b = 0; g_small_cl = 16; g_no_rowsel = 0; g_rowsel_probe = 0; g_mega = 0; g_mega_r = 2; g_mega_unit = 4; g_mega_spc = 24; g_mega_keep_l2 = 1; g_mega_dbg = 0;
     return 0;
   }
   if (!strcmp(name, "force_ldg")) { g_force_ldg = value; return 0; }
@@ -2287,6 +2295,7 @@ int specdec_set_option(const char* name, int value) {
   if (!strcmp(name, "tail_slots")) { g_tail_slots = value; return 0; }
   if (!strcmp(name, "tf_balance")) { g_tf_balance = value; return 0; }
   if (!strcmp(name, "static_rows")) { g_static_rows = value; return 0; }
+  if (!strcmp(name, "split_lists")) { g_split_lists = value; return 0; }
   if (!strcmp(name, "small_cl")) { g_small_cl = value; return 0; }
   if (!strcmp(name, "no_rowsel")) { g_no_rowsel = value; return 0; }
   if (!strcmp(name, "rowsel_probe")) { g_rowsel_probe = value; return 0; }

@@ -77,7 +77,11 @@ class _DeviceNGram(INgramStorage):
         ids = ids.to(device=self.device, dtype=torch.int64).contiguous()
         B, ml = ids.shape
         if lens is None:
-            lens = torch.full((B,), ml, dtype=torch.int32, device=self.device)
+            key = (B, ml)  # (full rows: the length vector is cached per shape)
+            cl = getattr(self, "_full_lens", None)
+            if cl is None or cl[0] != key:
+                self._full_lens = cl = (key, torch.full((B,), ml, dtype=torch.int32, device=self.device))
+            lens = cl[1]
         else:
             lens = lens.to(device=self.device, dtype=torch.int32).contiguous()
         if table_ids is not None:
@@ -109,7 +113,7 @@ class _DeviceNGram(INgramStorage):
             L.check(L.lib().specdec_ngram_lookup_chain(self._h, self._p(ids), self._p(lens), self._p(table_ids), B, ml,
                                                        gamma, self._p(fallback), self._p(drafts), self._p(known),
                                                        self._stream()), "specdec_ngram_lookup_chain")
-        return drafts, known.bool()
+        return drafts, known.view(torch.bool)  # (0/1 bytes written by the kernel: a view, not a conversion launch)
 
     def next_token(self, input_ids, lens=None, table_ids=None, fallback=None):
         d, k = self.lookup_chain(input_ids, 1, lens, table_ids, fallback)

@@ -722,9 +722,13 @@ def test_kept_list_sampling_equals_row_sweep(oracle_mod, mode, flags, sigma):
     r2 = sd.fused_verify(*args, flags=flags, **m)
     torch.cuda.synchronize()
     assert lib.specdec_set_option(b"no_klist", 0) == 0
-    for a, b_ in ((r1.n_accepted, r2.n_accepted), (r1.next_token, r2.next_token), (r1.p_tok, r2.p_tok), (r1.q_tok, r2.q_tok),
-                  (r1.accept_mask, r2.accept_mask), (r1.packed, r2.packed), (r1.next_prob, r2.next_prob)):
-        assert torch.equal(a, b_)
+    assert lib.specdec_set_option(b"split_lists", 1) == 0  # plan and list draw as two launches instead of plan_lists_kernel
+    r3 = sd.fused_verify(*args, flags=flags, **m)
+    torch.cuda.synchronize()
+    assert lib.specdec_set_option(b"split_lists", 0) == 0
+    for rr in (r2, r3):
+        for a in ("n_accepted", "next_token", "p_tok", "q_tok", "accept_mask", "packed", "next_prob"):
+            assert torch.equal(getattr(r1, a), getattr(rr, a)), a
     o = oracle_mod.verify(case["target"], case["draft"], case["draft_tokens"], case["u_accept"], case["u_sample"], flags=flags, **m)
     _assert_same(o, r1)
     # the drafter-side sampling op takes the same route
