@@ -120,7 +120,18 @@ SPECDEC_API int specdec_set_profile_events(void* ev_start, void* ev_mid, void* e
  *  "tma_ngram"=0 [1]        greedy n-gram verify on 16-bit rows: LDG arg-max kernel instead of the TMA row pipeline;
  *  "chunks"=n [2]           batch chunks pipelined on two streams (bf16/fp16, B >= 64 n; 1 = off; "no_overlap"=1 is
  *                           the same as "chunks"=1);  "p1_ctas"=k [3] row-kernel CTAs per SM for chunks > 0;
- *  "tf_ch"=k [20]           CTAs per sequence of tail_fused_kernel. */
+ *  "tf_ch"=k [20]           CTAs per sequence of the fused tail;  "tf_balance"=0 [1] slices NOT rounded to a multiple of
+ *                           8 segments (one per warp);
+ *  "tail_slots"=0 [1]       fused tail exchanges through atomics + counters (tail_fused_kernel) instead of
+ *                           self-validating words (tail_slots_kernel);
+ *  "static_rows"=1 [0]      TMA row kernel: rows assigned by blockIdx instead of claimed from a counter;
+ *  "small_b"=B [0]          batches of <= B sequences (plain modes) take the one-launch cluster-per-sequence kernel
+ *                           (measured slower than the pipeline: opt-in);  "small_cl"=8 [16] CTAs per cluster;
+ *  "no_rowsel"=1 [0]        masked modes skip the streamed selection kernel (rowsel_tma_kernel);
+ *  "no_klist"=1 [0]         masked modes draw by a sweep over the row instead of the kept-token lists;
+ *  "split_lists"=1 [0]      masked modes: plan and the list draw as two launches (plan_kernel + sample_lists_kernel);
+ *  "mega"=1 [0]             plain modes as one persistent cooperative launch (experimental, slower);
+ *  "reset"                  every option back to its default. */
 SPECDEC_API int specdec_set_option(const char* name, int value);
 /* Test hook: copies 16 device-side counters of nucleus_hist_kernel to out16 (host memory; synchronises):
  * [0..6] failed attempts by reason, [7] rows left to the slow path, [8] rows resolved, [9] attempts. */
