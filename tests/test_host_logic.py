@@ -189,3 +189,19 @@ def test_oracle_verify_semantics_small(oracle_mod):
     # top-k=1 on the drafter row makes q_tok = 0 for other tokens -> p/q = inf -> accept
     o = oracle_mod.verify(t, d, [[3, 1]], [[0.99, 0.99]], [0.5], top_k=1)
     assert o.q_tok[0, 0] == 0 and o.accept_mask[0, 0] == 1
+
+
+def test_every_library_option_is_documented_in_the_header():
+    """specdec_set_option names accepted by csrc/verify.cu == names documented in include/specdec_b200.h."""
+    src = open(os.path.join(ROOT, "speculative-decoding_b200", "csrc", "verify.cu")).read()
+    body = src[src.index("int specdec_set_option("):]
+    body = body[:body.index("\n}\n")]
+    accepted = set(re.findall(r'strcmp\(name, "(\w+)"\)', body))
+    hdr = open(os.path.join(ROOT, "include", "specdec_b200.h")).read()
+    doc = hdr[:hdr.index("SPECDEC_API int specdec_set_option")]
+    documented = set(re.findall(r'"(\w+)"(?:=\w+)?', doc[doc.rindex("/*"):]))
+    internal = {"mega_r", "mega_unit", "mega_spc", "mega_keep_l2", "mega_dbg", "rowsel_probe", "chunk0_pct"}  # tuning probes
+    assert accepted - internal <= documented, sorted(accepted - internal - documented)
+    lib = ctypes.CDLL(os.path.join(ROOT, "speculative-decoding_b200", "libspecdec_b200.so"))
+    lib.specdec_set_option.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    assert lib.specdec_set_option(b"no_such_option", 1) != 0 and lib.specdec_set_option(b"reset", 1) == 0
