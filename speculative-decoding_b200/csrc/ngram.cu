@@ -85,6 +85,7 @@ __device__ void ng_observe(GramSlot* g, int G, CountSlot* c, int C, const long l
   if (created) { g[gi].best_tok = (int)toks[0]; ++(*used); }
   for (int t = 0; t < m; ++t) {
     const int tok = (int)toks[t];
+    if (tok < 0) continue;  // padding of a batched update whose rows carry different numbers of tokens
     const int cnt = ng_bump(c, C, gi, tok);
     if (cnt < 0) { status[0] = 1; return; }
     if (tok == g[gi].best_tok) g[gi].best_cnt = cnt;              // incumbent's own count moves

@@ -124,13 +124,18 @@ def ngram_assisted_speculative_generate(
         input_ids[0, current_position + n] = x
 
         # update the ngram model (ngram_assisted.py:149-155)
-        for i in range(n):
-            ngramstorage.update(input_ids[..., :current_position + i], input_ids[..., current_position + i].reshape(1, 1))
+        if hasattr(ngramstorage, "update_chain"):
+            # device tables: the 2 (n + 1) updates of the step, in the reference's order, as ONE launch
+            ngramstorage.update_chain(input_ids[0], current_position, input_ids[0, current_position:current_position + n + 1],
+                                      fill[:n + 1] if filler_top_k > 1 else None)
+        else:  # any other INgramStorage: one call per update, as the reference does
+            for i in range(n):
+                ngramstorage.update(input_ids[..., :current_position + i], input_ids[..., current_position + i].reshape(1, 1))
+                if filler_top_k > 1:
+                    ngramstorage.update(input_ids[..., :current_position + i], fill[i].reshape(1, -1))
+            ngramstorage.update(input_ids[..., :current_position + n], torch.tensor([[x]], device=dev))
             if filler_top_k > 1:
-                ngramstorage.update(input_ids[..., :current_position + i], fill[i].reshape(1, -1))
-        ngramstorage.update(input_ids[..., :current_position + n], torch.tensor([[x]], device=dev))
-        if filler_top_k > 1:
-            ngramstorage.update(input_ids[..., :current_position + n], fill[n].reshape(1, -1))
+                ngramstorage.update(input_ids[..., :current_position + n], fill[n].reshape(1, -1))
 
         current_position += n + 1
         if x in stop_set:

@@ -126,6 +126,32 @@ class _DeviceNGram(INgramStorage):
             L.check(L.lib().specdec_ngram_update(self._h, self._p(ids), self._p(lens), self._p(table_ids), B, ml,
                                                  self._p(nt), nt.shape[1], self._stream()), "specdec_ngram_update")
 
+    def update_chain(self, ids_row, start: int, accepted, fillers=None, table_id: int = 0):
+        """The per-position updates of ONE n-gram-assisted step (ngram_assisted/ngram_assisted.py:149-155) as one launch:
+            for i in range(len(accepted)):
+                update(ids_row[:start + i], [accepted[i]]);  update(ids_row[:start + i], fillers[i])   # if fillers
+        The rows are applied in exactly this order by the table's thread (the arg-max rule of the reference depends on
+        the order of the updates); rows with fewer tokens are padded with -1, which the kernel skips.
+        accepted: int64 [n1] (device), fillers: int64 [>= n1, k] (device) or None."""
+        n1 = int(accepted.numel())
+        if n1 == 0:
+            return
+        dev = self.device
+        k = int(fillers.shape[1]) if fillers is not None else 1
+        rows = n1 * (2 if fillers is not None else 1)
+        nt = torch.full((rows, k), -1, dtype=torch.int64, device=dev)
+        pos = torch.arange(start, start + n1, dtype=torch.int32, device=dev)
+        if fillers is not None:
+            nt[0::2, 0] = accepted.to(dev)
+            nt[1::2] = fillers[:n1].to(dev)
+            lens = pos.repeat_interleave(2)
+        else:
+            nt[:, 0] = accepted.to(dev)
+            lens = pos
+        ids = ids_row.reshape(1, -1)[:, :start + n1].expand(rows, -1)
+        tabs = None if self.n_tables == 1 else torch.full((rows,), table_id, dtype=torch.int32, device=dev)
+        self.update(ids, nt, lens=lens, table_ids=tabs)
+
     def initialize(self, input_ids, lens=None, table_ids=None):
         ids, lens, table_ids, B, ml = self._prep(input_ids, lens, table_ids)
         with torch.cuda.device(self.device):

@@ -348,3 +348,40 @@ def test_graphed_verify_replays_match_eager_steps(oracle_mod):
     r = gv()
     e = sd.fused_verify(t, d, tk, None, None, seed=21, offset=8, **m)
     assert torch.equal(r.packed, e.packed)
+
+
+@pytest.mark.parametrize("one_level", [False, True])
+@pytest.mark.parametrize("with_fill", [False, True])
+def test_ngram_update_chain_equals_per_position_updates(one_level, with_fill):
+    """ngram_assisted/ngram_assisted.py:149-155: the 2 (n + 1) updates of a step as ONE launch == the reference's sequence
+    of update() calls (same order => same arg-max tokens), checked through the oracle dicts and the device tables."""
+    import specdec_b200 as sd
+    from oracle.ngram_oracle import NGramOracle
+    rng = np.random.RandomState(7)
+    V, n = 40, 4
+    cls = sd.OneLevelNGramStorage if one_level else sd.NGramStorage
+    a, b_ = cls(n, V, grams_per_table=4096, counts_per_table=8192), cls(n, V, grams_per_table=4096, counts_per_table=8192)
+    orc = NGramOracle(n, V, one_level)
+    seq = torch.from_numpy(rng.randint(0, 5, size=64)).cuda()
+    for st in (a, b_):
+        st.initialize(seq[:20].reshape(1, -1))
+    orc.initialize([seq[:20].cpu().numpy()])
+    pos = 20
+    for step in range(8):
+        n1 = int(rng.randint(1, 6))
+        fill = torch.from_numpy(rng.randint(0, 5, size=(n1, 3))).cuda() if with_fill else None
+        a.update_chain(seq, pos, seq[pos:pos + n1], fill)
+        for i in range(n1):
+            b_.update(seq[:pos + i].reshape(1, -1), seq[pos + i].reshape(1, 1))
+            orc.update([seq[:pos + i].cpu().numpy()], [[int(seq[pos + i])]])
+            if with_fill:
+                b_.update(seq[:pos + i].reshape(1, -1), fill[i].reshape(1, -1))
+                orc.update([seq[:pos + i].cpu().numpy()], [fill[i].cpu().tolist()])
+        pos += n1
+        fb = torch.zeros(1, 4, dtype=torch.long).cuda()
+        for L_ in (pos, pos - 1, 10):
+            da, ka = a.lookup_chain(seq[:L_].reshape(1, -1), 4, fallback=fb)
+            db, kb = b_.lookup_chain(seq[:L_].reshape(1, -1), 4, fallback=fb)
+            od, ok = orc.lookup_chain([seq[:L_].cpu().numpy()], 4, None, fb.cpu().numpy())
+            assert torch.equal(da, db) and torch.equal(ka, kb)
+            assert da.cpu().tolist() == od and ka.cpu().tolist() == ok
